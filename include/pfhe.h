@@ -1,0 +1,293 @@
+/*
+ * pfhe.h -- C-ABI of the B200-native polynomial-ring hot path (libpfhe_cuda.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative
+ * to /root/reference/crates/).  All compute runs in hand-written sm_100a CUDA
+ * kernels; there is no CPU fallback -- when no CUDA device is usable every
+ * call returns PFHE_ERR_CUDA.
+ *
+ * Conventions
+ *  - "host-slice shims" (`*_slice`, `*_slices`) take HOST memory exactly like
+ *    the reference traits do (`&mut [T]`, primus_data/src/traits.rs:20) and do
+ *    H2D -> kernel -> D2H internally, so a Rust `impl NttTable for CudaTable`
+ *    is a 1:1 forwarder.
+ *  - "device batch" entry points (`*_batch`, `*_dev`) take DEVICE pointers and a
+ *    `cudaStream_t` passed as `void*` (NULL = default stream); they are
+ *    stream-ordered, never synchronise and never allocate.
+ *  - Tables/handles are immutable after `create` and safe to use from many
+ *    host threads (NttTable: Send + Sync, primus_ntt/src/ntt/mod.rs:16).
+ *  - Hot-path calls are infallible in the reference (length mismatches are
+ *    debug_assert!, prime64/table.rs:543); here they return PFHE_ERR_INVALID_ARG
+ *    for NULL/zero-size misuse and PFHE_ERR_CUDA for launch failures.
+ *  - Layouts are the reference's flat element layouts: a batch of polynomials
+ *    is `[batch][N]`; DCRT/CRT polynomials are limb-major `[L][N]`
+ *    (primus_poly/src/dcrt/mod.rs:29,81-86); GGSW keys are
+ *    `[row k+1][level l][component k+1][limb L][N]` (primus_lattice/src/ggsw/dcrt.rs:14-31).
+ */
+#ifndef PFHE_H
+#define PFHE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..5 mirror NttError (primus_ntt/src/error.rs:7-49), 6..7 mirror
+ * RNSError (primus_rns/src/error.rs:7-20). */
+typedef enum {
+    PFHE_OK = 0,
+    PFHE_ERR_NO_PRIMITIVE_ROOT = 1, /* NttError::NoPrimitiveRoot   */
+    PFHE_ERR_DEGREE_CONVERSION = 2, /* NttError::DegreeConversionErr */
+    PFHE_ERR_DEGREE_TOO_LARGE = 3,  /* NttError::DegreeTooLarge    */
+    PFHE_ERR_NTT_TABLE = 4,         /* NttError::NttTableErr       */
+    PFHE_ERR_MODULUS_TOO_LARGE = 5, /* NttError::ModulusTooLarge   */
+    PFHE_ERR_RNS_EMPTY = 6,         /* RNSError::EmptyBase         */
+    PFHE_ERR_RNS_NOT_COPRIME = 7,   /* RNSError::CoPrimeError      */
+    PFHE_ERR_CUDA = 8,              /* CUDA runtime / no device    */
+    PFHE_ERR_INVALID_ARG = 9,
+    PFHE_ERR_UNSUPPORTED = 10
+} pfhe_status;
+
+const char *pfhe_status_string(pfhe_status s);
+/* Last CUDA error text seen by this thread (empty string when none). */
+const char *pfhe_last_cuda_error(void);
+/* Library/ABI version and the SM architecture the kernels were compiled for ("sm_100a"). */
+const char *pfhe_version(void);
+const char *pfhe_compiled_arch(void);
+/* Number of kernel launches issued by this library since load (all threads). */
+uint64_t pfhe_launch_count(void);
+
+/* Opaque handles */
+typedef struct pfhe_ntt32 pfhe_ntt32;   /* U32NttTable  primus_ntt/src/ntt/prime32/table.rs:37  */
+typedef struct pfhe_ntt64 pfhe_ntt64;   /* U64NttTable  primus_ntt/src/ntt/prime64/table.rs:41  */
+typedef struct pfhe_dcrt32 pfhe_dcrt32; /* U32DcrtTable primus_ntt/src/dcrt/prime32.rs          */
+typedef struct pfhe_dcrt64 pfhe_dcrt64; /* U64DcrtTable primus_ntt/src/dcrt/prime64.rs:11-128   */
+
+/* ===================================================================================== */
+/* NttTable (primus_ntt/src/ntt/mod.rs:16-113)                                            */
+/* ===================================================================================== */
+
+/* NttTable::new(log_n, modulus) -- prime64/table.rs:308-516, prime32/table.rs:185-343.
+ * Fails with NO_PRIMITIVE_ROOT when 2N does not divide q-1 (root.rs:72-81) and with
+ * MODULUS_TOO_LARGE when q >= 2^62 (u64, table.rs:318) / q >= 2^30 (u32, table.rs:195).
+ * Supported degrees: 1 <= log_n <= 14 (u64) / 15 (u32) (one polynomial per CTA in shared memory). */
+pfhe_status pfhe_ntt64_create(int device, uint32_t log_n, uint64_t q, pfhe_ntt64 **out);
+pfhe_status pfhe_ntt32_create(int device, uint32_t log_n, uint32_t q, pfhe_ntt32 **out);
+void pfhe_ntt64_destroy(pfhe_ntt64 *t);
+void pfhe_ntt32_destroy(pfhe_ntt32 *t);
+
+/* NttTable::poly_length and table constants (prime64/table.rs:41-113) */
+size_t pfhe_ntt64_poly_length(const pfhe_ntt64 *t);
+size_t pfhe_ntt32_poly_length(const pfhe_ntt32 *t);
+uint64_t pfhe_ntt64_modulus(const pfhe_ntt64 *t);
+uint32_t pfhe_ntt32_modulus(const pfhe_ntt32 *t);
+uint64_t pfhe_ntt64_root(const pfhe_ntt64 *t);      /* minimal primitive 2N-th root, root.rs:103-125 */
+uint32_t pfhe_ntt32_root(const pfhe_ntt32 *t);
+uint64_t pfhe_ntt64_inv_root(const pfhe_ntt64 *t);
+uint32_t pfhe_ntt32_inv_root(const pfhe_ntt32 *t);
+uint64_t pfhe_ntt64_inv_n(const pfhe_ntt64 *t);
+uint32_t pfhe_ntt32_inv_n(const pfhe_ntt32 *t);
+int pfhe_ntt64_device(const pfhe_ntt64 *t);
+int pfhe_ntt32_device(const pfhe_ntt32 *t);
+
+/* Host-slice shims: NttTable::{transform_slice, lazy_transform_slice, inverse_transform_slice,
+ * lazy_inverse_transform_slice} (ntt/mod.rs:53-91; prime64/table.rs:542-563).
+ * `poly` is HOST memory of N words, transformed in place (normal -> bit-reversed order forward,
+ * bit-reversed -> normal inverse).  lazy != 0 selects the lazy contract: forward accepts inputs
+ * in [0,4q), inverse in [0,2q); outputs are congruent mod q and inside the reference's lazy range
+ * (this implementation always returns canonical values, which satisfy both contracts). */
+pfhe_status pfhe_ntt64_transform_slice(const pfhe_ntt64 *t, uint64_t *poly, int lazy);
+pfhe_status pfhe_ntt32_transform_slice(const pfhe_ntt32 *t, uint32_t *poly, int lazy);
+pfhe_status pfhe_ntt64_inverse_transform_slice(const pfhe_ntt64 *t, uint64_t *values, int lazy);
+pfhe_status pfhe_ntt32_inverse_transform_slice(const pfhe_ntt32 *t, uint32_t *values, int lazy);
+/* Many polynomials in one call ([batch][N] HOST memory, in place); what the whole-ciphertext
+ * macros loop over (primus_lattice/src/macros/mod.rs:537-674). */
+pfhe_status pfhe_ntt64_transform_slices(const pfhe_ntt64 *t, uint64_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_ntt32_transform_slices(const pfhe_ntt32 *t, uint32_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_ntt64_inverse_transform_slices(const pfhe_ntt64 *t, uint64_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_ntt32_inverse_transform_slices(const pfhe_ntt32 *t, uint32_t *polys, size_t batch, int lazy);
+
+/* NttTable::{transform_monomial, transform_coeff_one_monomial, transform_coeff_minus_one_monomial}
+ * (ntt/mod.rs:93-112; prime64/table.rs:565-651): NTT(coeff * X^degree) into `values` (HOST, N words). */
+pfhe_status pfhe_ntt64_transform_monomial(const pfhe_ntt64 *t, uint64_t coeff, size_t degree, uint64_t *values);
+pfhe_status pfhe_ntt32_transform_monomial(const pfhe_ntt32 *t, uint32_t coeff, size_t degree, uint32_t *values);
+pfhe_status pfhe_ntt64_transform_coeff_one_monomial(const pfhe_ntt64 *t, size_t degree, uint64_t *values);
+pfhe_status pfhe_ntt32_transform_coeff_one_monomial(const pfhe_ntt32 *t, size_t degree, uint32_t *values);
+pfhe_status pfhe_ntt64_transform_coeff_minus_one_monomial(const pfhe_ntt64 *t, size_t degree, uint64_t *values);
+pfhe_status pfhe_ntt32_transform_coeff_minus_one_monomial(const pfhe_ntt32 *t, size_t degree, uint32_t *values);
+
+/* Device batch API (stream ordered, in place, `dev` = [batch][N] DEVICE words). */
+pfhe_status pfhe_ntt64_forward_batch(const pfhe_ntt64 *t, uint64_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_forward_batch(const pfhe_ntt32 *t, uint32_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_ntt64_inverse_batch(const pfhe_ntt64 *t, uint64_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_inverse_batch(const pfhe_ntt32 *t, uint32_t *dev, size_t batch, void *stream);
+/* Out-of-place variants (src -> dst, src untouched). */
+pfhe_status pfhe_ntt64_forward_batch_to(const pfhe_ntt64 *t, const uint64_t *src, uint64_t *dst, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_forward_batch_to(const pfhe_ntt32 *t, const uint32_t *src, uint32_t *dst, size_t batch, void *stream);
+pfhe_status pfhe_ntt64_inverse_batch_to(const pfhe_ntt64 *t, const uint64_t *src, uint64_t *dst, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_inverse_batch_to(const pfhe_ntt32 *t, const uint32_t *src, uint32_t *dst, size_t batch, void *stream);
+/* Monomial transforms on the device: degrees[batch] (device, each < 2N) -> out [batch][N];
+ * coeff as in transform_monomial. */
+pfhe_status pfhe_ntt64_monomial_batch(const pfhe_ntt64 *t, uint64_t coeff, const uint32_t *degrees, uint64_t *out, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_monomial_batch(const pfhe_ntt32 *t, uint32_t coeff, const uint32_t *degrees, uint32_t *out, size_t batch, void *stream);
+
+/* Fused negacyclic product  c = inv(fwd(a) .* fwd(b))  in Z_q[X]/(X^N+1): the composition callers
+ * make from transform_slice + NttPolynomial::mul_assign + inverse_transform_slice
+ * (primus_lattice/src/rlwe/coeff.rs:92-122; primus_poly/src/ntt/mul.rs:84-90).  a,b,c = [batch][N]
+ * device; c may alias a or b.  Host variant takes HOST pointers. */
+pfhe_status pfhe_ntt64_polymul_batch(const pfhe_ntt64 *t, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, void *stream);
+pfhe_status pfhe_ntt32_polymul_batch(const pfhe_ntt32 *t, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, void *stream);
+pfhe_status pfhe_ntt64_polymul_slices(const pfhe_ntt64 *t, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch);
+pfhe_status pfhe_ntt32_polymul_slices(const pfhe_ntt32 *t, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch);
+
+/* ===================================================================================== */
+/* DcrtTable (primus_ntt/src/dcrt/mod.rs:19-135): L independent limb tables, layout [L][N] */
+/* ===================================================================================== */
+pfhe_status pfhe_dcrt64_create(int device, uint32_t log_n, const uint64_t *moduli, size_t count, pfhe_dcrt64 **out);
+pfhe_status pfhe_dcrt32_create(int device, uint32_t log_n, const uint32_t *moduli, size_t count, pfhe_dcrt32 **out);
+void pfhe_dcrt64_destroy(pfhe_dcrt64 *t);
+void pfhe_dcrt32_destroy(pfhe_dcrt32 *t);
+size_t pfhe_dcrt64_poly_length(const pfhe_dcrt64 *t);
+size_t pfhe_dcrt32_poly_length(const pfhe_dcrt32 *t);
+size_t pfhe_dcrt64_moduli_count(const pfhe_dcrt64 *t);
+size_t pfhe_dcrt32_moduli_count(const pfhe_dcrt32 *t);
+size_t pfhe_dcrt64_crt_poly_length(const pfhe_dcrt64 *t);
+size_t pfhe_dcrt32_crt_poly_length(const pfhe_dcrt32 *t);
+/* ntt_tables()/iter(): borrow the i-th limb table (owned by the DCRT handle). */
+const pfhe_ntt64 *pfhe_dcrt64_ntt_table(const pfhe_dcrt64 *t, size_t limb);
+const pfhe_ntt32 *pfhe_dcrt32_ntt_table(const pfhe_dcrt32 *t, size_t limb);
+/* host-slice shims over [batch][L][N] HOST words (batch = 1 is the trait method) */
+pfhe_status pfhe_dcrt64_transform_slices(const pfhe_dcrt64 *t, uint64_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_dcrt32_transform_slices(const pfhe_dcrt32 *t, uint32_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_dcrt64_inverse_transform_slices(const pfhe_dcrt64 *t, uint64_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_dcrt32_inverse_transform_slices(const pfhe_dcrt32 *t, uint32_t *polys, size_t batch, int lazy);
+/* device batch: dev = [batch][L][N] */
+pfhe_status pfhe_dcrt64_forward_batch(const pfhe_dcrt64 *t, uint64_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_dcrt32_forward_batch(const pfhe_dcrt32 *t, uint32_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_dcrt64_inverse_batch(const pfhe_dcrt64 *t, uint64_t *dev, size_t batch, void *stream);
+pfhe_status pfhe_dcrt32_inverse_batch(const pfhe_dcrt32 *t, uint32_t *dev, size_t batch, void *stream);
+/* RNS polynomial product per limb: DcrtTable::transform + DcrtPolynomial::mul_assign
+ * (primus_poly/src/dcrt/mul.rs:176-187) + inverse, fused. */
+pfhe_status pfhe_dcrt64_polymul_batch(const pfhe_dcrt64 *t, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch, void *stream);
+pfhe_status pfhe_dcrt32_polymul_batch(const pfhe_dcrt32 *t, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch, void *stream);
+
+/* ===================================================================================== */
+/* Pointwise modular slice operators on DEVICE memory.                                    */
+/* Traits: primus_reduce/src/slice_ops.rs:63-230; bodies primus_modulus/src/barrett/slice.rs:185-295 */
+/* -> common/compact/slice.rs:106-365.  `q` must satisfy 1 < q < 2^(BITS-2)                */
+/* (BarrettModulus::new, primus_modulus/src/barrett/mod.rs:39-43).  Inputs in [0,q).       */
+/* `limbs`/`n`: the slices are [rows][limbs][n] with modulus moduli[limb] per limb         */
+/* (DcrtPolynomial ops, primus_poly/src/dcrt/mul.rs:176-187, dcrt/mod.rs:105-123);         */
+/* single-modulus slices use limbs = 1, rows*n = length.                                   */
+/* ===================================================================================== */
+typedef enum {
+    PFHE_OP_MUL = 0,         /* out = a*b          reduce_mul_slice_to / _assign (out==a)        */
+    PFHE_OP_ADD_MUL = 1,     /* out = out + a*b    reduce_add_mul_slice_assign                   */
+    PFHE_OP_SUB_MUL = 2,     /* out = out - a*b    reduce_sub_mul_slice_assign                   */
+    PFHE_OP_MUL_ADD = 3,     /* out = a*b + c      reduce_mul_add_slice_to                       */
+    PFHE_OP_ADD = 4,         /* out = a + b        reduce_add_slice_to                           */
+    PFHE_OP_SUB = 5,         /* out = a - b        reduce_sub_slice_to                           */
+    PFHE_OP_NEG = 6,         /* out = -a           reduce_neg_slice_to                           */
+    PFHE_OP_MUL_SCALAR = 7,  /* out = a*s          reduce_mul_scalar_slice_to                    */
+    PFHE_OP_ADD_MUL_SCALAR = 8, /* out = out + a*s reduce_add_mul_scalar_slice_assign            */
+    PFHE_OP_FACTOR_MUL = 9,  /* out = f*a  (Shoup) FactorSliceOps::factor_mul_slice_to (primus_factor/src/ops.rs:58-118) */
+    PFHE_OP_ADD_FACTOR_MUL = 10, /* out += f*a     add_factor_mul_slice_assign (common/slice.rs:61-70)   */
+    PFHE_OP_SUB_FACTOR_MUL = 11  /* out -= f*a     sub_factor_mul_slice_assign                   */
+} pfhe_slice_op;
+
+/* One entry point per word size; `scalars` (HOST, `limbs` words) holds s / f per limb for the
+ * scalar and factor ops (ignored otherwise); `b`, `c` may be NULL when the op does not read them. */
+pfhe_status pfhe_mod64_slice_op(pfhe_slice_op op, const uint64_t *moduli, size_t limbs, const uint64_t *scalars,
+                                const uint64_t *a, const uint64_t *b, const uint64_t *c, uint64_t *out,
+                                size_t rows, size_t n, void *stream);
+pfhe_status pfhe_mod32_slice_op(pfhe_slice_op op, const uint32_t *moduli, size_t limbs, const uint32_t *scalars,
+                                const uint32_t *a, const uint32_t *b, const uint32_t *c, uint32_t *out,
+                                size_t rows, size_t n, void *stream);
+/* Host-slice shims of the same operators (HOST pointers; H2D -> kernel -> D2H). */
+pfhe_status pfhe_mod64_slice_op_host(pfhe_slice_op op, const uint64_t *moduli, size_t limbs, const uint64_t *scalars,
+                                     const uint64_t *a, const uint64_t *b, const uint64_t *c, uint64_t *out,
+                                     size_t rows, size_t n);
+pfhe_status pfhe_mod32_slice_op_host(pfhe_slice_op op, const uint32_t *moduli, size_t limbs, const uint32_t *scalars,
+                                     const uint32_t *a, const uint32_t *b, const uint32_t *c, uint32_t *out,
+                                     size_t rows, size_t n);
+
+/* ===================================================================================== */
+/* Gadget decomposition and RNS limb handling                                             */
+/* ===================================================================================== */
+
+/* ApproxSignedBasis::new(Some(q), log_basis, reverse_length) geometry
+ * (primus_decompose/src/primitive/basis.rs:47-176).  levels_in = 0 means the full length
+ * floor(bitlen(q)/log_basis).  Outputs the decompose length and drop bits. */
+pfhe_status pfhe_basis64_geometry(uint64_t q, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits);
+pfhe_status pfhe_basis32_geometry(uint32_t q, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits);
+
+/* init_value_carry_slice + OnceSignedDecomposer::decompose_slice_to for every level, fused
+ * (basis.rs:254-406; primitive/common.rs:219-273).  values: [count] device words in [0,q);
+ * digits: [levels][count] device words, LSB level first, each digit canonical in [0,q)
+ * (negative digits are q - |d|). */
+pfhe_status pfhe_decompose64_batch(uint64_t q, uint32_t log_basis, uint32_t levels_in, const uint64_t *values,
+                                   uint64_t *digits, size_t count, void *stream);
+pfhe_status pfhe_decompose32_batch(uint32_t q, uint32_t log_basis, uint32_t levels_in, const uint32_t *values,
+                                   uint32_t *digits, size_t count, void *stream);
+
+/* RNSBase::wrapping_decompose_small_values_to (primus_rns/src/base.rs:279-315): centred lift of
+ * small values in [0, small_modulus) to every limb; out is modulus-major [limbs][count]. */
+pfhe_status pfhe_rns64_lift_small_batch(const uint64_t *moduli, size_t limbs, uint64_t small_modulus,
+                                        const uint64_t *small, uint64_t *out, size_t count, void *stream);
+pfhe_status pfhe_rns32_lift_small_batch(const uint32_t *moduli, size_t limbs, uint32_t small_modulus,
+                                        const uint32_t *small, uint32_t *out, size_t count, void *stream);
+
+/* ===================================================================================== */
+/* External product and blind rotation                                                    */
+/* ===================================================================================== */
+
+/* Single-modulus (L = 1) GGSW external product, fused per ciphertext:
+ *   out_c = [inv]( sum_{r<=k} sum_{l<levels} fwd(digit_l(in_r)) .* key[r][l][c] )
+ * = CrtGlwe::mul_dcrt_ggsw_to (primus_lattice/src/glwe/crt.rs:200-227) -> gadget product
+ * (glwe/dcrt.rs:178-255) -> MAC (glwe/dcrt.rs:108-126) [+ into_coeff_form, macros/mod.rs:892-937
+ * when to_coeff != 0].  key: device [k+1][levels][k+1][N] in NTT domain, shared by the batch;
+ * in/out: device [batch][k+1][N]; in is coefficient domain, canonical. */
+pfhe_status pfhe_ggsw64_external_product_batch(const pfhe_ntt64 *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,
+                                               const uint64_t *key, const uint64_t *in, uint64_t *out,
+                                               size_t batch, int to_coeff, void *stream);
+pfhe_status pfhe_ggsw32_external_product_batch(const pfhe_ntt32 *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,
+                                               const uint32_t *key, const uint32_t *in, uint32_t *out,
+                                               size_t batch, int to_coeff, void *stream);
+
+/* Blind rotation composed from the reference's primitives (the reference has
+ * no blind rotation: mul_monomial_assign primus_poly/src/poly/mul.rs:74-99, external product as
+ * above, RLWE add).  bsk: device [n_lwe][2][levels][2][N] NTT domain; lwe: device
+ * [batch][n_lwe+1] uint32 (a_0..a_{n-1}, b) already in Z_{2N}; test_vector: device [N];
+ * acc_out: device [batch][2][N] (a then b polynomial), canonical coefficients. */
+pfhe_status pfhe_blind_rotate64_batch(const pfhe_ntt64 *t, uint32_t log_basis, uint32_t levels_in, const uint64_t *bsk,
+                                      uint32_t n_lwe, const uint32_t *lwe, const uint64_t *test_vector,
+                                      uint64_t *acc_out, size_t batch, void *stream);
+pfhe_status pfhe_blind_rotate32_batch(const pfhe_ntt32 *t, uint32_t log_basis, uint32_t levels_in, const uint32_t *bsk,
+                                      uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
+                                      uint32_t *acc_out, size_t batch, void *stream);
+/* Rlwe::extract_lwe (primus_lattice/src/rlwe/coeff.rs:264-288): rlwe [batch][2][N] -> lwe [batch][N+1] */
+pfhe_status pfhe_extract_lwe64_batch(uint64_t q, const uint64_t *rlwe, uint64_t *lwe, size_t n, size_t batch, void *stream);
+pfhe_status pfhe_extract_lwe32_batch(uint32_t q, const uint32_t *rlwe, uint32_t *lwe, size_t n, size_t batch, void *stream);
+
+/* ===================================================================================== */
+/* Plumbing for hosts without a CUDA binding of their own (the Rust FFI crate, tests)      */
+/* ===================================================================================== */
+pfhe_status pfhe_device_count(int *count);
+pfhe_status pfhe_malloc(int device, size_t bytes, void **dev_ptr);
+pfhe_status pfhe_free(int device, void *dev_ptr);
+pfhe_status pfhe_memcpy_h2d(int device, void *dev_dst, const void *host_src, size_t bytes, void *stream);
+pfhe_status pfhe_memcpy_d2h(int device, void *host_dst, const void *dev_src, size_t bytes, void *stream);
+pfhe_status pfhe_stream_synchronize(int device, void *stream);
+
+/* Integer-pipe microbenchmark used to measure the modmul roofline denominator
+ * (SURVEY.md 8d): runs `iters` dependent Shoup modmuls per thread in registers on
+ * `blocks` x 256 threads and returns elapsed milliseconds via *ms. kind: 0 = u32, 1 = u64. */
+pfhe_status pfhe_modmul_microbench(int device, int kind, uint32_t blocks, uint32_t iters, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFHE_H */

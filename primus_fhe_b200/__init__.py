@@ -1,0 +1,10 @@
+"""primus_fhe_b200 -- B200-native (sm_100a) implementation of primus-fhe's polynomial-ring hot path.
+
+The package holds only what the path needs: `csrc/` (CUDA kernels + the C-ABI of include/pfhe.h),
+`build.py` (in-tree nvcc build) and `api.py` (host-side mirror of the reference's trait surface).
+"""
+from ._cabi import PfheError, LIB_PATH, declared_symbols, launch_count  # noqa: F401
+from .api import (  # noqa: F401
+    ApproxSignedBasis, BarrettModulus, RNSBase, U32DcrtTable, U32NttTable, U64DcrtTable, U64NttTable,
+    device_count, extract_lwe_batch, modmul_microbench,
+)

@@ -1,0 +1,408 @@
+"""Host-side mirror of the reference's operator surface for the polynomial-ring hot path.
+
+Python stands in for the Rust FFI crate here (no Rust toolchain in this image):
+every class forwards 1:1 to the C-ABI in include/pfhe.h, exactly as `impl NttTable for CudaU64NttTable`
+would.  Names, argument meaning and error behaviour follow the reference:
+
+  U32NttTable / U64NttTable     trait NttTable            primus_ntt/src/ntt/mod.rs:16-113
+  U32DcrtTable / U64DcrtTable   trait DcrtTable           primus_ntt/src/dcrt/mod.rs:19-135
+  BarrettModulus (slice ops)    ReduceMulSlice & co       primus_reduce/src/slice_ops.rs:63-230
+  ShoupFactor (slice ops)       FactorSliceOps            primus_factor/src/ops.rs:58-118
+  ApproxSignedBasis             decompose_slice_to        primus_decompose/src/primitive/basis.rs:12-407
+  RNSBase.wrapping_decompose_small_values_to              primus_rns/src/base.rs:279-315
+  external_product / blind_rotate                         primus_lattice/src/glwe/crt.rs:200-227, SURVEY App. A.6
+
+Host-slice methods take numpy arrays / CPU torch tensors (in place, like `&mut [T]`); `*_batch`
+methods take CUDA torch tensors and run on torch's current stream.  PyTorch is plumbing only
+(device memory, streams); all arithmetic happens in libpfhe_cuda.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import PfheError, check, lib
+
+OP_MUL, OP_ADD_MUL, OP_SUB_MUL, OP_MUL_ADD, OP_ADD, OP_SUB, OP_NEG = range(7)
+OP_MUL_SCALAR, OP_ADD_MUL_SCALAR, OP_FACTOR_MUL, OP_ADD_FACTOR_MUL, OP_SUB_FACTOR_MUL = range(7, 12)
+
+
+def _ct(bits):
+    return C.c_uint32 if bits == 32 else C.c_uint64
+
+
+def _np_dtype(bits):
+    return np.uint32 if bits == 32 else np.uint64
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _host_ptr(x, bits, n_words=None):
+    """Pointer to a contiguous HOST buffer of `bits`-wide words (numpy array or CPU torch tensor)."""
+    if _is_torch(x):
+        if x.is_cuda:
+            raise TypeError("host-slice methods take host memory; use the *_batch methods for CUDA tensors")
+        if not x.is_contiguous() or x.element_size() * 8 != bits:
+            raise TypeError("expected a contiguous tensor of %d-bit words" % bits)
+        if n_words is not None and x.numel() != n_words:
+            raise ValueError(f"length mismatch: {x.numel()} != {n_words}")
+        return C.c_void_p(x.data_ptr())
+    if not isinstance(x, np.ndarray) or x.dtype.itemsize * 8 != bits or not x.flags.c_contiguous:
+        raise TypeError("expected a C-contiguous numpy array of %d-bit words" % bits)
+    if n_words is not None and x.size != n_words:
+        raise ValueError(f"length mismatch: {x.size} != {n_words}")
+    return x.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(x, bits, n_words=None):
+    if not _is_torch(x) or not x.is_cuda:
+        raise TypeError("*_batch methods take CUDA torch tensors")
+    if not x.is_contiguous() or x.element_size() * 8 != bits:
+        raise TypeError("expected a contiguous CUDA tensor of %d-bit words" % bits)
+    if n_words is not None and x.numel() != n_words:
+        raise ValueError(f"length mismatch: {x.numel()} != {n_words}")
+    return C.c_void_p(x.data_ptr())
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().pfhe_device_count(C.byref(n)))
+    return n.value
+
+
+class _NttTable:
+    """NttTable (primus_ntt/src/ntt/mod.rs:16-113) backed by device-resident tables."""
+    bits = 64
+
+    def __init__(self, log_n: int, modulus: int, device: int = 0):
+        self._h = C.c_void_p()
+        self._p = f"pfhe_ntt{self.bits}_"
+        f = getattr(lib(), self._p + "create")
+        f.argtypes = [C.c_int, C.c_uint32, _ct(self.bits), C.c_void_p]
+        check(f(device, log_n, int(modulus), C.byref(self._h)))
+        self.log_n, self.n, self.q, self.device = log_n, 1 << log_n, int(modulus), device
+
+    @classmethod
+    def new(cls, log_n, modulus, device=0):
+        return cls(log_n, modulus, device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+            f(h); self._h = None
+
+    def _scalar(self, name):
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p]; f.restype = _ct(self.bits)
+        return int(f(self._h))
+
+    def poly_length(self) -> int:
+        f = getattr(lib(), self._p + "poly_length"); f.argtypes = [C.c_void_p]; f.restype = C.c_size_t
+        return int(f(self._h))
+
+    def modulus(self): return self._scalar("modulus")
+    def root(self): return self._scalar("root")
+    def inv_root(self): return self._scalar("inv_root")
+    def inv_n(self): return self._scalar("inv_n")
+
+    # ---- host-slice trait methods (in place) ----
+    def _host1(self, name, poly, lazy):
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        check(f(self._h, _host_ptr(poly, self.bits, self.n), int(lazy)))
+
+    def transform_slice(self, poly): self._host1("transform_slice", poly, 0)
+    def lazy_transform_slice(self, poly): self._host1("transform_slice", poly, 1)
+    def inverse_transform_slice(self, values): self._host1("inverse_transform_slice", values, 0)
+    def lazy_inverse_transform_slice(self, values): self._host1("inverse_transform_slice", values, 1)
+
+    def transform_inplace(self, poly):
+        self.transform_slice(poly); return poly
+
+    def inverse_transform_inplace(self, values):
+        self.inverse_transform_slice(values); return values
+
+    def _hostn(self, name, polys, lazy=0):
+        size = polys.numel() if _is_torch(polys) else polys.size
+        if size % self.n:
+            raise ValueError("batch buffer is not a multiple of the polynomial length")
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(self._h, _host_ptr(polys, self.bits), size // self.n, lazy))
+
+    def transform_slices(self, polys): self._hostn("transform_slices", polys)
+    def inverse_transform_slices(self, polys): self._hostn("inverse_transform_slices", polys)
+
+    def transform_monomial(self, coeff, degree, values=None):
+        values = np.empty(self.n, dtype=_np_dtype(self.bits)) if values is None else values
+        f = getattr(lib(), self._p + "transform_monomial")
+        f.argtypes = [C.c_void_p, _ct(self.bits), C.c_size_t, C.c_void_p]
+        check(f(self._h, int(coeff), int(degree), _host_ptr(values, self.bits, self.n)))
+        return values
+
+    def transform_coeff_one_monomial(self, degree, values=None):
+        values = np.empty(self.n, dtype=_np_dtype(self.bits)) if values is None else values
+        f = getattr(lib(), self._p + "transform_coeff_one_monomial"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._h, int(degree), _host_ptr(values, self.bits, self.n))); return values
+
+    def transform_coeff_minus_one_monomial(self, degree, values=None):
+        values = np.empty(self.n, dtype=_np_dtype(self.bits)) if values is None else values
+        f = getattr(lib(), self._p + "transform_coeff_minus_one_monomial"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._h, int(degree), _host_ptr(values, self.bits, self.n))); return values
+
+    def polymul_slices(self, a, b, c=None):
+        if c is None:
+            c = np.empty_like(a)
+        size = a.numel() if _is_torch(a) else a.size
+        f = getattr(lib(), self._p + "polymul_slices"); f.argtypes = [C.c_void_p] * 4 + [C.c_size_t]
+        check(f(self._h, _host_ptr(a, self.bits), _host_ptr(b, self.bits, size), _host_ptr(c, self.bits, size), size // self.n))
+        return c
+
+    # ---- device batch API (CUDA torch tensors, current stream) ----
+    def _batch(self, name, dev):
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(dev, self.bits), dev.numel() // self.n, _stream()))
+
+    def forward_batch(self, dev): self._batch("forward_batch", dev)
+    def inverse_batch(self, dev): self._batch("inverse_batch", dev)
+
+    def forward_batch_to(self, src, dst):
+        f = getattr(lib(), self._p + "forward_batch_to"); f.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(src, self.bits), _dev_ptr(dst, self.bits, src.numel()), src.numel() // self.n, _stream()))
+
+    def inverse_batch_to(self, src, dst):
+        f = getattr(lib(), self._p + "inverse_batch_to"); f.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(src, self.bits), _dev_ptr(dst, self.bits, src.numel()), src.numel() // self.n, _stream()))
+
+    def polymul_batch(self, a, b, c):
+        f = getattr(lib(), self._p + "polymul_batch"); f.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(a, self.bits), _dev_ptr(b, self.bits, a.numel()), _dev_ptr(c, self.bits, a.numel()),
+                a.numel() // self.n, _stream()))
+
+    def monomial_batch(self, coeff, degrees, out):
+        f = getattr(lib(), self._p + "monomial_batch")
+        f.argtypes = [C.c_void_p, _ct(self.bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._h, int(coeff), _dev_ptr(degrees, 32), _dev_ptr(out, self.bits, degrees.numel() * self.n),
+                degrees.numel(), _stream()))
+
+    # ---- lattice ops on this table's ring (L = 1) ----
+    def external_product_batch(self, k, log_basis, levels, key, glwe_in, out, to_coeff=True):
+        """GGSW external product, fused (primus_lattice/src/glwe/crt.rs:200-227 [+ into_coeff_form])."""
+        f = getattr(lib(), f"pfhe_ggsw{self.bits}_external_product_batch")
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        batch = glwe_in.numel() // ((k + 1) * self.n)
+        check(f(self._h, k, log_basis, levels or 0, _dev_ptr(key, self.bits), _dev_ptr(glwe_in, self.bits),
+                _dev_ptr(out, self.bits, glwe_in.numel()), batch, int(to_coeff), _stream()))
+
+    def blind_rotate_batch(self, log_basis, levels, bsk, n_lwe, lwe, test_vector, acc_out):
+        """Composed blind rotation."""
+        f = getattr(lib(), f"pfhe_blind_rotate{self.bits}_batch")
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        batch = lwe.numel() // (n_lwe + 1)
+        check(f(self._h, log_basis, levels or 0, _dev_ptr(bsk, self.bits), n_lwe, _dev_ptr(lwe, 32),
+                _dev_ptr(test_vector, self.bits, self.n), _dev_ptr(acc_out, self.bits, batch * 2 * self.n), batch, _stream()))
+
+
+class U64NttTable(_NttTable):
+    bits = 64
+
+
+class U32NttTable(_NttTable):
+    bits = 32
+
+
+class _DcrtTable:
+    """DcrtTable (primus_ntt/src/dcrt/mod.rs:19-135): limb-major [L][N]."""
+    bits = 64
+
+    def __init__(self, log_n: int, moduli, device: int = 0):
+        self._h = C.c_void_p()
+        self._p = f"pfhe_dcrt{self.bits}_"
+        self.moduli = [int(m) for m in moduli]
+        arr = (_ct(self.bits) * max(1, len(self.moduli)))(*self.moduli)
+        f = getattr(lib(), self._p + "create")
+        f.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(device, log_n, arr, len(self.moduli), C.byref(self._h)))
+        self.log_n, self.n = log_n, 1 << log_n
+
+    @classmethod
+    def new(cls, log_n, moduli, device=0):
+        return cls(log_n, moduli, device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+            f(h); self._h = None
+
+    def _size(self, name):
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p]; f.restype = C.c_size_t
+        return int(f(self._h))
+
+    def poly_length(self): return self._size("poly_length")
+    def moduli_count(self): return self._size("moduli_count")
+    def crt_poly_length(self): return self._size("crt_poly_length")
+
+    def _hostn(self, name, polys):
+        size = polys.numel() if _is_torch(polys) else polys.size
+        unit = self.n * len(self.moduli)
+        if size % unit:
+            raise ValueError("buffer is not a multiple of the CRT polynomial length")
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(self._h, _host_ptr(polys, self.bits), size // unit, 0))
+
+    def transform_slice(self, poly): self._hostn("transform_slices", poly)
+    def inverse_transform_slice(self, poly): self._hostn("inverse_transform_slices", poly)
+    lazy_transform_slice = transform_slice
+    lazy_inverse_transform_slice = inverse_transform_slice
+
+    def _batch(self, name, dev):
+        unit = self.n * len(self.moduli)
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(dev, self.bits), dev.numel() // unit, _stream()))
+
+    def forward_batch(self, dev): self._batch("forward_batch", dev)
+    def inverse_batch(self, dev): self._batch("inverse_batch", dev)
+
+    def polymul_batch(self, a, b, c):
+        unit = self.n * len(self.moduli)
+        f = getattr(lib(), self._p + "polymul_batch"); f.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(a, self.bits), _dev_ptr(b, self.bits, a.numel()), _dev_ptr(c, self.bits, a.numel()),
+                a.numel() // unit, _stream()))
+
+
+class U64DcrtTable(_DcrtTable):
+    bits = 64
+
+
+class U32DcrtTable(_DcrtTable):
+    bits = 32
+
+
+def _slice_op(bits, op, moduli, scalars, a, b, c, out, rows, n, host):
+    L = len(moduli)
+    m = (_ct(bits) * L)(*[int(x) for x in moduli])
+    s = (_ct(bits) * L)(*[int(x) for x in scalars]) if scalars is not None else None
+    ptr = (lambda x: _host_ptr(x, bits)) if host else (lambda x: _dev_ptr(x, bits))
+    args = [op, m, L, s, ptr(a), ptr(b) if b is not None else None, ptr(c) if c is not None else None, ptr(out), rows, n]
+    f = getattr(lib(), f"pfhe_mod{bits}_slice_op" + ("_host" if host else ""))
+    f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p] + [C.c_void_p] * 4 + [C.c_size_t, C.c_size_t] + ([] if host else [C.c_void_p])
+    if not host:
+        args.append(_stream())
+    check(f(*args))
+
+
+class BarrettModulus:
+    """Slice operators of a BarrettModulus (primus_modulus/src/barrett/slice.rs:185-295) on device or host slices.
+    With several moduli it is the per-limb DcrtPolynomial form (slices are [rows][L][n])."""
+
+    def __init__(self, value, bits=64, n=None):
+        self.moduli = [int(v) for v in (value if isinstance(value, (list, tuple)) else [value])]
+        self.bits, self.n = bits, n
+        for q in self.moduli:
+            if q <= 1:
+                raise ValueError("modulus can't be 0 or 1.")
+            if q >> (bits - 2):
+                raise ValueError("modulus is too large.")
+
+    def value(self): return self.moduli[0]
+
+    def _run(self, op, a, b=None, c=None, out=None, scalars=None):
+        host = not (_is_torch(a) and a.is_cuda)
+        size = a.numel() if _is_torch(a) else a.size
+        L = len(self.moduli)
+        n = self.n if self.n else size // L
+        rows = size // (L * n)
+        _slice_op(self.bits, op, self.moduli, scalars, a, b, c, out, rows, n, host)
+        return out
+
+    def reduce_mul_slice_to(self, a, b, out): return self._run(OP_MUL, a, b, None, out)
+    def reduce_mul_slice_assign(self, a, b): return self._run(OP_MUL, a, b, None, a)
+    def reduce_add_mul_slice_assign(self, acc, a, b): return self._run(OP_ADD_MUL, a, b, None, acc)
+    def reduce_sub_mul_slice_assign(self, acc, a, b): return self._run(OP_SUB_MUL, a, b, None, acc)
+    def reduce_mul_add_slice_to(self, a, b, c, out): return self._run(OP_MUL_ADD, a, b, c, out)
+    def reduce_add_slice_to(self, a, b, out): return self._run(OP_ADD, a, b, None, out)
+    def reduce_sub_slice_to(self, a, b, out): return self._run(OP_SUB, a, b, None, out)
+    def reduce_neg_slice_to(self, a, out): return self._run(OP_NEG, a, None, None, out)
+
+    def reduce_mul_scalar_slice_to(self, a, scalar, out):
+        return self._run(OP_MUL_SCALAR, a, None, None, out, self._sc(scalar))
+
+    def reduce_add_mul_scalar_slice_assign(self, acc, a, scalar):
+        return self._run(OP_ADD_MUL_SCALAR, a, None, None, acc, self._sc(scalar))
+
+    def _sc(self, s):
+        return [int(x) for x in s] if isinstance(s, (list, tuple)) else [int(s)] * len(self.moduli)
+
+    # FactorSliceOps with Shoup factors (primus_factor/src/ops.rs:58-118); factor value(s) per limb
+    def factor_mul_slice_to(self, factor, rhs, out): return self._run(OP_FACTOR_MUL, rhs, None, None, out, self._sc(factor))
+    def add_factor_mul_slice_assign(self, factor, acc, rhs): return self._run(OP_ADD_FACTOR_MUL, rhs, None, None, acc, self._sc(factor))
+    def sub_factor_mul_slice_assign(self, factor, acc, rhs): return self._run(OP_SUB_FACTOR_MUL, rhs, None, None, acc, self._sc(factor))
+
+
+class ApproxSignedBasis:
+    """ApproxSignedBasis::new(Some(q), log_basis, reverse_length) + fused slice decomposition
+    (primus_decompose/src/primitive/basis.rs:47-176, :254-406; primitive/common.rs:219-273)."""
+
+    def __init__(self, modulus, log_basis, reverse_length=None, bits=64):
+        self.q, self.bits, self._log_basis, self._rev = int(modulus), bits, log_basis, reverse_length or 0
+        lv, dr = C.c_uint32(0), C.c_uint32(0)
+        f = getattr(lib(), f"pfhe_basis{bits}_geometry")
+        f.argtypes = [_ct(bits), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        check(f(self.q, log_basis, self._rev, C.byref(lv), C.byref(dr)))
+        self._levels, self._drop = lv.value, dr.value
+
+    def decompose_length(self): return self._levels
+    def drop_bits(self): return self._drop
+    def log_basis(self): return self._log_basis
+    def basis_value(self): return 1 << self._log_basis
+    def scalars(self): return [1 << (self._drop + l * self._log_basis) for l in range(self._levels)]
+
+    def decompose_batch(self, values, digits):
+        """values: CUDA [count]; digits: CUDA [levels][count], LSB level first, canonical mod q."""
+        f = getattr(lib(), f"pfhe_decompose{self.bits}_batch")
+        f.argtypes = [_ct(self.bits), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self.q, self._log_basis, self._rev, _dev_ptr(values, self.bits),
+                _dev_ptr(digits, self.bits, values.numel() * self._levels), values.numel(), _stream()))
+
+
+class RNSBase:
+    """The limb-handling part of RNSBase that is on the hot path (primus_rns/src/base.rs:279-315)."""
+
+    def __init__(self, moduli, bits=64):
+        if len(moduli) == 0:
+            raise PfheError(6)
+        self.moduli, self.bits = [int(m) for m in moduli], bits
+
+    def moduli_count(self): return len(self.moduli)
+
+    def wrapping_decompose_small_values_to(self, small, multi_residues, small_modulus):
+        L = len(self.moduli)
+        m = (_ct(self.bits) * L)(*self.moduli)
+        f = getattr(lib(), f"pfhe_rns{self.bits}_lift_small_batch")
+        f.argtypes = [C.c_void_p, C.c_size_t, _ct(self.bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(m, L, int(small_modulus), _dev_ptr(small, self.bits), _dev_ptr(multi_residues, self.bits, small.numel() * L),
+                small.numel(), _stream()))
+
+
+def extract_lwe_batch(q, rlwe, lwe, n, bits=64):
+    """Rlwe::extract_lwe (primus_lattice/src/rlwe/coeff.rs:264-288) over a batch."""
+    f = getattr(lib(), f"pfhe_extract_lwe{bits}_batch")
+    f.argtypes = [_ct(bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    batch = rlwe.numel() // (2 * n)
+    check(f(int(q), _dev_ptr(rlwe, bits), _dev_ptr(lwe, bits, batch * (n + 1)), n, batch, _stream()))
+
+
+def modmul_microbench(kind: int, blocks: int, iters: int, device: int = 0) -> float:
+    ms = C.c_float(0)
+    f = lib().pfhe_modmul_microbench
+    f.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    check(f(device, kind, blocks, iters, C.byref(ms)))
+    return ms.value

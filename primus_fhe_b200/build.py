@@ -1,0 +1,62 @@
+"""Build libpfhe_cuda.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension machinery).
+
+    python -m primus_fhe_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libpfhe_cuda.so")
+SOURCES = ["ntt.cu", "pointwise.cu", "lattice.cu", "capi.cu"]
+HEADERS = ["modarith.cuh", "ntt_core.cuh", "internal.hpp", "host_math.hpp"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr",
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "pfhe.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(f"---- {src} ----\n{out}\n")
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    # visibility: the C-ABI symbols are exported through the default-visibility attribute below
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,675 @@
+// capi.cu -- the C-ABI (include/pfhe.h): handle construction, table upload, host-slice shims with a
+// pipelined H2D -> kernel -> D2H path, and the thin device-batch forwarders.
+// No CPU compute path exists here: every transform / product is a kernel launch (no CPU fallback).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host_math.hpp"
+#include "internal.hpp"
+#include "pfhe.h"
+
+namespace pfhe {
+int lattice_loge(int bits, int log_n);
+
+static thread_local std::string t_last_cuda_error;
+static pfhe_status cuda_fail(cudaError_t e) {
+    t_last_cuda_error = cudaGetErrorString(e);
+    cudaGetLastError();  // clear sticky-free errors
+    if (e == cudaErrorNotSupported) return PFHE_ERR_UNSUPPORTED;
+    return PFHE_ERR_CUDA;
+}
+#define PFHE_CUDA(expr)                                    \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return pfhe::cuda_fail(_e); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = prev == dev || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (ok && prev >= 0) {
+            int cur = -1;
+            cudaGetDevice(&cur);
+            if (cur != prev) cudaSetDevice(prev);
+        }
+    }
+};
+
+// per-thread copy streams (thread safe by construction)
+constexpr int kPipe = 3;
+struct ThreadStreams {
+    std::vector<std::vector<cudaStream_t>> per_device;
+    cudaError_t get(int device, cudaStream_t *out) {
+        if ((int)per_device.size() <= device) per_device.resize(device + 1);
+        auto &v = per_device[device];
+        if (v.empty()) {
+            v.resize(kPipe);
+            for (auto &s : v) {
+                cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+                if (e != cudaSuccess) {
+                    v.clear();
+                    return e;
+                }
+            }
+        }
+        for (int i = 0; i < kPipe; i++) out[i] = v[i];
+        return cudaSuccess;
+    }
+};
+static thread_local ThreadStreams t_streams;
+
+template <typename T> struct NttHandle {
+    int device = 0;
+    host::HostTables<T> h;
+    DevNtt<T> dev{};      // register-pass layout for the standalone NTT kernels
+    DevNtt<T> dev_lat{};  // same table, per-pass layout for the lattice kernels (loge == 0: unsupported size)
+    void *blob = nullptr;
+};
+
+template <typename T>
+static void fill_pass_tables(const host::HostTables<T> &h, int loge, std::vector<typename Word<T>::Pair> &fwd,
+                             std::vector<typename Word<T>::Pair> &inv) {
+    using Pair = typename Word<T>::Pair;
+    const int logn = (int)h.log_n;
+    const size_t n = h.n;
+    PlanRt pl(logn, loge);
+    fwd.assign(pl.total(), Pair{});
+    inv.assign(pl.total(), Pair{});
+    for (int p = 0; p < pl.npass; p++) {
+        const int ns = pl.nstages(p), fb = pl.fb(p), nh = pl.nh(p), off = pl.pass_offset(p), s0 = pl.s0(p);
+        for (int ls = 0; ls < ns; ls++) {
+            const int jb = loge - 1 - ls;
+            const int b = fb + jb;  // index bit of this stage
+            const size_t inv_base = 1 + n - (n >> b);
+            for (int jp = 0; jp < (1 << ls); jp++) {
+                for (int high = 0; high < nh; high++) {
+                    const size_t blk = ((size_t)high << ls) | (size_t)jp;
+                    const size_t slot = (size_t)off + (size_t)((1 << ls) - 1 + jp) * nh + high;
+                    const size_t fi = ((size_t)1 << (s0 + ls)) + blk;
+                    fwd[slot].x = h.roots[fi];
+                    fwd[slot].y = h.roots_q[fi];
+                    const size_t ii = inv_base + blk;
+                    if (b == logn - 1) {  // final inverse stage: inv_n * inv_roots[n-1]
+                        inv[slot].x = h.inv_n_w;
+                        inv[slot].y = h.inv_n_w_q;
+                    } else {
+                        inv[slot].x = h.inv_roots[ii];
+                        inv[slot].y = h.inv_roots_q[ii];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, typename H> static pfhe_status create_handle(int device, uint32_t log_n, T q, H **out) {
+    using Pair = typename Word<T>::Pair;
+    constexpr int BITS = sizeof(T) * 8;
+    if (!out) return PFHE_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (log_n == 0 || log_n + 1 >= (uint32_t)BITS) return PFHE_ERR_DEGREE_TOO_LARGE;
+    T root;
+    if (!host::min_primitive_root<T>(log_n + 1, q, root)) return PFHE_ERR_NO_PRIMITIVE_ROOT;  // root.rs:72-81
+    if ((q >> (BITS - 2)) != 0) return PFHE_ERR_MODULUS_TOO_LARGE;                           // table.rs:318 / :195
+    const uint32_t max_log_n = BITS == 64 ? 14 : 15;  // one polynomial per CTA in shared memory
+    if (log_n > max_log_n) return PFHE_ERR_DEGREE_TOO_LARGE;
+    int count = 0;
+    PFHE_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return PFHE_ERR_INVALID_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+
+    auto *hd = new (std::nothrow) H();
+    if (!hd) return PFHE_ERR_NTT_TABLE;
+    hd->device = device;
+    host::build_tables<T>(log_n, q, root, hd->h);
+    const auto &h = hd->h;
+    const size_t n = h.n;
+    std::vector<Pair> fwd(n), inv(n), fp, ip, fpl, ipl;
+    for (size_t k = 0; k < n; k++) {
+        fwd[k].x = h.roots[k];
+        fwd[k].y = h.roots_q[k];
+        inv[k].x = h.inv_roots[k];
+        inv[k].y = h.inv_roots_q[k];
+    }
+    inv[n - 1].x = h.inv_n_w;
+    inv[n - 1].y = h.inv_n_w_q;
+    const int loge = choose_loge(BITS, (int)log_n), loge_lat = lattice_loge(BITS, (int)log_n);
+    if (loge) fill_pass_tables<T>(h, loge, fp, ip);
+    if (loge_lat) fill_pass_tables<T>(h, loge_lat, fpl, ipl);
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t sz_pair = sizeof(Pair);
+    size_t off_fwd = 0, off_inv = align(off_fwd + n * sz_pair), off_fp = align(off_inv + n * sz_pair),
+           off_ip = align(off_fp + fp.size() * sz_pair), off_fpl = align(off_ip + ip.size() * sz_pair),
+           off_ipl = align(off_fpl + fpl.size() * sz_pair), off_ord = align(off_ipl + ipl.size() * sz_pair),
+           total = align(off_ord + 2 * n * sizeof(T));
+    std::vector<unsigned char> stage(total, 0);
+    memcpy(stage.data() + off_fwd, fwd.data(), n * sz_pair);
+    memcpy(stage.data() + off_inv, inv.data(), n * sz_pair);
+    if (!fp.empty()) memcpy(stage.data() + off_fp, fp.data(), fp.size() * sz_pair);
+    if (!ip.empty()) memcpy(stage.data() + off_ip, ip.data(), ip.size() * sz_pair);
+    if (!fpl.empty()) memcpy(stage.data() + off_fpl, fpl.data(), fpl.size() * sz_pair);
+    if (!ipl.empty()) memcpy(stage.data() + off_ipl, ipl.data(), ipl.size() * sz_pair);
+    memcpy(stage.data() + off_ord, h.ordinal.data(), 2 * n * sizeof(T));
+    cudaError_t e = cudaMalloc(&hd->blob, total);
+    if (e == cudaSuccess) e = cudaMemcpy(hd->blob, stage.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (hd->blob) cudaFree(hd->blob);
+        delete hd;
+        return cuda_fail(e);
+    }
+    unsigned char *base = static_cast<unsigned char *>(hd->blob);
+    DevNtt<T> d{};
+    d.q = q;
+    d.two_q = (T)(q << 1);
+    d.inv_n = h.inv_n;
+    d.inv_n_q = h.inv_n_q;
+    d.br.q = q;
+    host::barrett_ratio<T>(q, d.br.r0, d.br.r1);
+    d.log_n = log_n;
+    d.loge = (uint32_t)loge;
+    d.fwd = reinterpret_cast<const Pair *>(base + off_fwd);
+    d.inv = reinterpret_cast<const Pair *>(base + off_inv);
+    d.fwd_pass = reinterpret_cast<const Pair *>(base + off_fp);
+    d.inv_pass = reinterpret_cast<const Pair *>(base + off_ip);
+    d.ordinal = reinterpret_cast<const T *>(base + off_ord);
+    hd->dev = d;
+    hd->dev_lat = d;
+    hd->dev_lat.loge = (uint32_t)loge_lat;
+    hd->dev_lat.fwd_pass = reinterpret_cast<const Pair *>(base + off_fpl);
+    hd->dev_lat.inv_pass = reinterpret_cast<const Pair *>(base + off_ipl);
+    *out = hd;
+    return PFHE_OK;
+}
+
+template <typename H> static void destroy_handle(H *h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->blob) cudaFree(h->blob);
+    delete h;
+}
+
+template <typename T> struct DcrtHandle {
+    int device = 0;
+    std::vector<NttHandle<T> *> limbs;
+    DevNtt<T> *d_tables = nullptr;  // device array of the limb tables
+};
+
+// Pipelined host <-> device processing of `units` independent work items (`in_bytes`/`out_bytes` each).
+// launch(dev_in_chunks[], dev_out, n_units, stream).
+template <typename LaunchF>
+static pfhe_status pipelined(int device, const void *const *host_in, int n_in, const size_t *in_bytes, void *host_out, size_t out_bytes,
+                             size_t units, LaunchF launch, int out_alias = -1) {
+    if (units == 0) return PFHE_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    cudaStream_t st[kPipe];
+    PFHE_CUDA(t_streams.get(device, st));
+    size_t per_unit = out_alias >= 0 ? 0 : out_bytes;  // out_alias: the kernel updates input region #out_alias in place
+    for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];
+    // chunk so that each stage moves ~16 MiB; at least one unit
+    size_t chunk = (size_t)(16u << 20) / (per_unit ? per_unit : 1);
+    if (chunk == 0) chunk = 1;
+    if (chunk > units) chunk = units;
+    const int nbuf = (int)((units + chunk - 1) / chunk < (size_t)kPipe ? (units + chunk - 1) / chunk : kPipe);
+    void *dbuf[kPipe] = {nullptr, nullptr, nullptr};
+    pfhe_status status = PFHE_OK;
+    for (int i = 0; i < nbuf; i++) {
+        cudaError_t e = cudaMallocAsync(&dbuf[i], chunk * per_unit, st[i]);
+        if (e != cudaSuccess) {
+            status = cuda_fail(e);
+            break;
+        }
+    }
+    if (status == PFHE_OK) {
+        size_t done = 0;
+        for (int c = 0; done < units; c++) {
+            const int b = c % nbuf;
+            const size_t nu = units - done < chunk ? units - done : chunk;
+            unsigned char *base = static_cast<unsigned char *>(dbuf[b]);
+            const void *din[4] = {nullptr, nullptr, nullptr, nullptr};
+            size_t off = 0;
+            cudaError_t e = cudaSuccess;
+            for (int i = 0; i < n_in && e == cudaSuccess; i++) {
+                din[i] = base + off;
+                e = cudaMemcpyAsync(base + off, static_cast<const unsigned char *>(host_in[i]) + done * in_bytes[i], nu * in_bytes[i],
+                                    cudaMemcpyHostToDevice, st[b]);
+                off += chunk * in_bytes[i];
+            }
+            void *dout = out_alias >= 0 ? const_cast<void *>(din[out_alias]) : static_cast<void *>(base + off);
+            if (e == cudaSuccess) e = launch(din, dout, nu, st[b]);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(static_cast<unsigned char *>(host_out) + done * out_bytes, dout, nu * out_bytes, cudaMemcpyDeviceToHost,
+                                    st[b]);
+            if (e != cudaSuccess) {
+                status = cuda_fail(e);
+                break;
+            }
+            done += nu;
+        }
+    }
+    for (int i = 0; i < nbuf; i++) {
+        if (dbuf[i]) cudaFreeAsync(dbuf[i], st[i]);
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && status == PFHE_OK) status = cuda_fail(e);
+    }
+    return status;
+}
+
+template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd) {
+    if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
+    const size_t bytes = sizeof(T) << t->h.log_n;
+    const void *ins[1] = {polys};
+    const size_t inb[1] = {bytes};
+    // in place on the device: the "out" region doubles as the input region (n_in = 0 inputs + copy in manually)
+    return pipelined(t->device, ins, 1, inb, polys, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
+        return launch_ntt<T>(t->dev, nullptr, 1, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu, fwd, s);
+    });
+}
+
+template <typename T> static pfhe_status host_polymul(const NttHandle<T> *t, const T *a, const T *b, T *c, size_t batch) {
+    if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;
+    const size_t bytes = sizeof(T) << t->h.log_n;
+    const void *ins[2] = {a, b};
+    const size_t inb[2] = {bytes, bytes};
+    return pipelined(t->device, ins, 2, inb, c, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
+        return launch_polymul<T>(t->dev, nullptr, 1, static_cast<const T *>(din[0]), static_cast<const T *>(din[1]), static_cast<T *>(dout),
+                                 nu, s);
+    });
+}
+
+template <typename T> static pfhe_status host_monomial(const NttHandle<T> *t, T coeff, size_t degree, T *values) {
+    if (!t || !values) return PFHE_ERR_INVALID_ARG;
+    if (degree >= 2 * t->h.n || coeff >= t->h.q) return PFHE_ERR_INVALID_ARG;
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    cudaStream_t st[kPipe];
+    PFHE_CUDA(t_streams.get(t->device, st));
+    const size_t bytes = sizeof(T) << t->h.log_n;
+    void *d = nullptr;
+    PFHE_CUDA(cudaMallocAsync(&d, bytes + 256, st[0]));
+    uint32_t *ddeg = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(d) + bytes);
+    const uint32_t deg32 = (uint32_t)degree;
+    cudaError_t e = cudaMemcpyAsync(ddeg, &deg32, sizeof(deg32), cudaMemcpyHostToDevice, st[0]);
+    if (e == cudaSuccess) e = launch_monomial<T>(t->dev, coeff, ddeg, static_cast<T *>(d), 1, st[0]);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d, bytes, cudaMemcpyDeviceToHost, st[0]);
+    cudaFreeAsync(d, st[0]);
+    cudaError_t e2 = cudaStreamSynchronize(st[0]);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (e2 != cudaSuccess) return cuda_fail(e2);
+    return PFHE_OK;
+}
+
+template <typename T> static pfhe_status make_limb_consts(const T *moduli, size_t limbs, const T *scalars, int op, LimbConsts<T> &lc) {
+    constexpr int BITS = sizeof(T) * 8;
+    if (!moduli || limbs == 0 || limbs > (size_t)kMaxLimbs) return PFHE_ERR_INVALID_ARG;
+    const bool needs_scalar = op == PFHE_OP_MUL_SCALAR || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_FACTOR_MUL ||
+                              op == PFHE_OP_ADD_FACTOR_MUL || op == PFHE_OP_SUB_FACTOR_MUL;
+    if (needs_scalar && !scalars) return PFHE_ERR_INVALID_ARG;
+    for (size_t i = 0; i < limbs; i++) {
+        const T q = moduli[i];
+        if (q <= 1) return PFHE_ERR_INVALID_ARG;
+        if ((q >> (BITS - 2)) != 0) return PFHE_ERR_MODULUS_TOO_LARGE;  // BarrettModulus::new, barrett/mod.rs:39-43
+        lc.br[i].q = q;
+        host::barrett_ratio<T>(q, lc.br[i].r0, lc.br[i].r1);
+        lc.scalar[i] = needs_scalar ? scalars[i] : 0;
+        if (needs_scalar && scalars[i] >= q) return PFHE_ERR_INVALID_ARG;
+        lc.scalar_q[i] = needs_scalar ? host::shoup_quot<T>(scalars[i], q) : 0;
+    }
+    return PFHE_OK;
+}
+
+template <typename T>
+static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
+                                size_t n, void *stream) {
+    if (op < 0 || op > PFHE_OP_SUB_FACTOR_MUL) return PFHE_ERR_INVALID_ARG;
+    if (rows * n == 0) return PFHE_OK;
+    if (!a || !out) return PFHE_ERR_INVALID_ARG;
+    if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
+    if (op == PFHE_OP_MUL_ADD && !c) return PFHE_ERR_INVALID_ARG;
+    LimbConsts<T> lc;
+    pfhe_status s = make_limb_consts<T>(moduli, limbs, scalars, op, lc);
+    if (s != PFHE_OK) return s;
+    PFHE_CUDA(launch_slice_op<T>(op, lc, (int)limbs, a, b, c, out, rows, n, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+
+}  // namespace pfhe
+
+using namespace pfhe;
+
+struct pfhe_ntt32 : NttHandle<uint32_t> {};
+struct pfhe_ntt64 : NttHandle<uint64_t> {};
+struct pfhe_dcrt32 : DcrtHandle<uint32_t> {};
+struct pfhe_dcrt64 : DcrtHandle<uint64_t> {};
+
+namespace pfhe {
+
+template <typename T, typename H, typename D>
+static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size_t count, D **out) {
+    if (!out) return PFHE_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!moduli || count == 0) return PFHE_ERR_RNS_EMPTY;
+    if (count > (size_t)kMaxLimbs) return PFHE_ERR_INVALID_ARG;
+    auto *d = new (std::nothrow) D();
+    if (!d) return PFHE_ERR_NTT_TABLE;
+    d->device = device;
+    pfhe_status s = PFHE_OK;
+    for (size_t i = 0; i < count && s == PFHE_OK; i++) {
+        H *h = nullptr;
+        s = create_handle<T, H>(device, log_n, moduli[i], &h);
+        if (s == PFHE_OK) d->limbs.push_back(h);
+    }
+    if (s == PFHE_OK) {
+        DeviceGuard guard(device);
+        std::vector<DevNtt<T>> tabs;
+        for (auto *h : d->limbs) tabs.push_back(h->dev);
+        cudaError_t e = cudaMalloc(&d->d_tables, tabs.size() * sizeof(DevNtt<T>));
+        if (e == cudaSuccess) e = cudaMemcpy(d->d_tables, tabs.data(), tabs.size() * sizeof(DevNtt<T>), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) s = cuda_fail(e);
+    }
+    if (s != PFHE_OK) {
+        for (auto *h : d->limbs) destroy_handle(static_cast<H *>(h));
+        if (d->d_tables) cudaFree(d->d_tables);
+        delete d;
+        return s;
+    }
+    *out = d;
+    return PFHE_OK;
+}
+
+template <typename T, typename D> static pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd) {
+    if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
+    const size_t L = t->limbs.size();
+    const size_t bytes = (sizeof(T) << t->limbs[0]->h.log_n) * L;
+    const void *ins[1] = {polys};
+    const size_t inb[1] = {bytes};
+    return pipelined(t->device, ins, 1, inb, polys, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
+        return launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)L, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu * L, fwd, s);
+    });
+}
+
+template <typename T>
+static pfhe_status slice_op_host(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
+                                 size_t n) {
+    if (op < 0 || op > PFHE_OP_SUB_FACTOR_MUL) return PFHE_ERR_INVALID_ARG;
+    if (rows * n == 0) return PFHE_OK;
+    if (!a || !out) return PFHE_ERR_INVALID_ARG;
+    if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
+    if (op == PFHE_OP_MUL_ADD && !c) return PFHE_ERR_INVALID_ARG;
+    LimbConsts<T> lc;
+    pfhe_status s = make_limb_consts<T>(moduli, limbs, scalars, op, lc);
+    if (s != PFHE_OK) return s;
+    const bool acc = op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_ADD_FACTOR_MUL ||
+                     op == PFHE_OP_SUB_FACTOR_MUL;
+    const bool rb = op <= PFHE_OP_SUB, rc = op == PFHE_OP_MUL_ADD;
+    const size_t bytes = sizeof(T) * limbs * n;
+    const void *ins[4];
+    size_t inb[4];
+    int n_in = 0, ia = 0, ib = -1, ic = -1, io = -1;
+    ins[n_in] = a; inb[n_in] = bytes; ia = n_in++;
+    if (rb) { ins[n_in] = b; inb[n_in] = bytes; ib = n_in++; }
+    if (rc) { ins[n_in] = c; inb[n_in] = bytes; ic = n_in++; }
+    if (acc) { ins[n_in] = out; inb[n_in] = bytes; io = n_in++; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return pipelined(dev, ins, n_in, inb, out, bytes, rows, [&](const void *const *din, void *dout, size_t nu, cudaStream_t st) {
+        return launch_slice_op<T>(op, lc, (int)limbs, static_cast<const T *>(din[ia]), ib >= 0 ? static_cast<const T *>(din[ib]) : nullptr,
+                                  ic >= 0 ? static_cast<const T *>(din[ic]) : nullptr, static_cast<T *>(dout), nu, n, st);
+    }, io);
+}
+
+template <typename T, typename H>
+static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,
+                            int to_coeff, void *stream) {
+    if (!t || ((!key || !in || !out) && batch)) return PFHE_ERR_INVALID_ARG;
+    GadgetParams<T> g;
+    if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
+    if (t->dev_lat.loge == 0 || k < 1 || k > 2) return PFHE_ERR_UNSUPPORTED;
+    PFHE_CUDA(launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+template <typename T, typename H>
+static pfhe_status blind_rot(const H *t, uint32_t log_basis, uint32_t levels_in, const T *bsk, uint32_t n_lwe, const uint32_t *lwe,
+                             const T *tv, T *acc_out, size_t batch, void *stream) {
+    if (!t || ((!bsk || !lwe || !tv || !acc_out) && batch)) return PFHE_ERR_INVALID_ARG;
+    GadgetParams<T> g;
+    if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
+    if (t->dev_lat.loge == 0) return PFHE_ERR_UNSUPPORTED;
+    PFHE_CUDA(launch_blind_rotate<T>(t->dev_lat, g, bsk, n_lwe, lwe, tv, acc_out, batch, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+
+}  // namespace pfhe
+
+extern "C" {
+
+const char *pfhe_status_string(pfhe_status s) {
+    switch (s) {
+        case PFHE_OK: return "Ok";
+        case PFHE_ERR_NO_PRIMITIVE_ROOT: return "NoPrimitiveRoot";
+        case PFHE_ERR_DEGREE_CONVERSION: return "DegreeConversionErr";
+        case PFHE_ERR_DEGREE_TOO_LARGE: return "DegreeTooLarge";
+        case PFHE_ERR_NTT_TABLE: return "NttTableErr";
+        case PFHE_ERR_MODULUS_TOO_LARGE: return "ModulusTooLarge";
+        case PFHE_ERR_RNS_EMPTY: return "EmptyBase";
+        case PFHE_ERR_RNS_NOT_COPRIME: return "CoPrimeError";
+        case PFHE_ERR_CUDA: return "CudaError";
+        case PFHE_ERR_INVALID_ARG: return "InvalidArgument";
+        case PFHE_ERR_UNSUPPORTED: return "Unsupported";
+    }
+    return "Unknown";
+}
+const char *pfhe_last_cuda_error(void) { return t_last_cuda_error.c_str(); }
+const char *pfhe_version(void) { return "primus_fhe_b200 0.1.0 (abi 1)"; }
+const char *pfhe_compiled_arch(void) { return "sm_100a"; }
+uint64_t pfhe_launch_count(void) { return g_launches.load(); }
+
+#define PFHE_DEFINE_WORD(B, T)                                                                                                        \
+    pfhe_status pfhe_ntt##B##_create(int device, uint32_t log_n, T q, pfhe_ntt##B **out) {                                            \
+        return create_handle<T, pfhe_ntt##B>(device, log_n, q, out);                                                                  \
+    }                                                                                                                                 \
+    void pfhe_ntt##B##_destroy(pfhe_ntt##B *t) { destroy_handle(t); }                                                                 \
+    size_t pfhe_ntt##B##_poly_length(const pfhe_ntt##B *t) { return t ? t->h.n : 0; }                                                 \
+    T pfhe_ntt##B##_modulus(const pfhe_ntt##B *t) { return t ? t->h.q : 0; }                                                          \
+    T pfhe_ntt##B##_root(const pfhe_ntt##B *t) { return t ? t->h.root : 0; }                                                          \
+    T pfhe_ntt##B##_inv_root(const pfhe_ntt##B *t) { return t ? t->h.inv_root : 0; }                                                  \
+    T pfhe_ntt##B##_inv_n(const pfhe_ntt##B *t) { return t ? t->h.inv_n : 0; }                                                        \
+    int pfhe_ntt##B##_device(const pfhe_ntt##B *t) { return t ? t->device : -1; }                                                     \
+    pfhe_status pfhe_ntt##B##_transform_slice(const pfhe_ntt##B *t, T *poly, int) { return host_transform<T>(t, poly, 1, true); }     \
+    pfhe_status pfhe_ntt##B##_inverse_transform_slice(const pfhe_ntt##B *t, T *v, int) { return host_transform<T>(t, v, 1, false); }  \
+    pfhe_status pfhe_ntt##B##_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int) {                                       \
+        return host_transform<T>(t, p, batch, true);                                                                                  \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_inverse_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int) {                               \
+        return host_transform<T>(t, p, batch, false);                                                                                 \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_transform_monomial(const pfhe_ntt##B *t, T coeff, size_t degree, T *values) {                           \
+        return host_monomial<T>(t, coeff, degree, values);                                                                            \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_transform_coeff_one_monomial(const pfhe_ntt##B *t, size_t degree, T *values) {                          \
+        return host_monomial<T>(t, (T)1, degree, values);                                                                             \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_transform_coeff_minus_one_monomial(const pfhe_ntt##B *t, size_t degree, T *values) {                    \
+        return t ? host_monomial<T>(t, (T)(t->h.q - 1), degree, values) : PFHE_ERR_INVALID_ARG;                                       \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_forward_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
+        if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, true, static_cast<cudaStream_t>(stream)));                       \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_inverse_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
+        if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, false, static_cast<cudaStream_t>(stream)));                      \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_forward_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
+        if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
+        PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, true, static_cast<cudaStream_t>(stream)));                       \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_inverse_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
+        if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
+        PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, false, static_cast<cudaStream_t>(stream)));                      \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_monomial_batch(const pfhe_ntt##B *t, T coeff, const uint32_t *degrees, T *out, size_t batch,            \
+                                             void *stream) {                                                                          \
+        if (!t || ((!degrees || !out) && batch) || coeff >= t->h.q) return PFHE_ERR_INVALID_ARG;                                      \
+        PFHE_CUDA(launch_monomial<T>(t->dev, coeff, degrees, out, batch, static_cast<cudaStream_t>(stream)));                         \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_polymul_batch(const pfhe_ntt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {         \
+        if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
+        PFHE_CUDA(launch_polymul<T>(t->dev, nullptr, 1, a, b, c, batch, static_cast<cudaStream_t>(stream)));                          \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ntt##B##_polymul_slices(const pfhe_ntt##B *t, const T *a, const T *b, T *c, size_t batch) {                      \
+        return host_polymul<T>(t, a, b, c, batch);                                                                                    \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_create(int device, uint32_t log_n, const T *moduli, size_t count, pfhe_dcrt##B **out) {                \
+        return create_dcrt<T, pfhe_ntt##B, pfhe_dcrt##B>(device, log_n, moduli, count, out);                                          \
+    }                                                                                                                                 \
+    void pfhe_dcrt##B##_destroy(pfhe_dcrt##B *t) {                                                                                    \
+        if (!t) return;                                                                                                               \
+        for (auto *h : t->limbs) destroy_handle(static_cast<pfhe_ntt##B *>(h));                                                       \
+        if (t->d_tables) {                                                                                                            \
+            DeviceGuard guard(t->device);                                                                                             \
+            cudaFree(t->d_tables);                                                                                                    \
+        }                                                                                                                             \
+        delete t;                                                                                                                     \
+    }                                                                                                                                 \
+    size_t pfhe_dcrt##B##_poly_length(const pfhe_dcrt##B *t) { return t ? t->limbs[0]->h.n : 0; }                                     \
+    size_t pfhe_dcrt##B##_moduli_count(const pfhe_dcrt##B *t) { return t ? t->limbs.size() : 0; }                                     \
+    size_t pfhe_dcrt##B##_crt_poly_length(const pfhe_dcrt##B *t) { return t ? t->limbs.size() * t->limbs[0]->h.n : 0; }               \
+    const pfhe_ntt##B *pfhe_dcrt##B##_ntt_table(const pfhe_dcrt##B *t, size_t limb) {                                                 \
+        return (t && limb < t->limbs.size()) ? static_cast<const pfhe_ntt##B *>(t->limbs[limb]) : nullptr;                            \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int) {                                     \
+        return dcrt_host_transform<T>(t, p, batch, true);                                                                             \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_inverse_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int) {                             \
+        return dcrt_host_transform<T>(t, p, batch, false);                                                                            \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_forward_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
+        if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_CUDA(launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), true,         \
+                                static_cast<cudaStream_t>(stream)));                                                                  \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_inverse_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
+        if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_CUDA(launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), false,        \
+                                static_cast<cudaStream_t>(stream)));                                                                  \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_polymul_batch(const pfhe_dcrt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {       \
+        if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
+        PFHE_CUDA(launch_polymul<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), a, b, c, batch * t->limbs.size(),            \
+                                    static_cast<cudaStream_t>(stream)));                                                              \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_slice_op(pfhe_slice_op op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b,     \
+                                       const T *c, T *out, size_t rows, size_t n, void *stream) {                                     \
+        return slice_op_dev<T>((int)op, moduli, limbs, scalars, a, b, c, out, rows, n, stream);                                       \
+    }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_slice_op_host(pfhe_slice_op op, const T *moduli, size_t limbs, const T *scalars, const T *a,            \
+                                            const T *b, const T *c, T *out, size_t rows, size_t n) {                                  \
+        return slice_op_host<T>((int)op, moduli, limbs, scalars, a, b, c, out, rows, n);                                              \
+    }                                                                                                                                 \
+    pfhe_status pfhe_basis##B##_geometry(T q, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits) {        \
+        GadgetParams<T> g;                                                                                                            \
+        if (!make_gadget<T>(q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;                                                 \
+        if (levels) *levels = g.levels;                                                                                               \
+        if (drop_bits) *drop_bits = g.drop_bits;                                                                                      \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_decompose##B##_batch(T q, uint32_t log_basis, uint32_t levels_in, const T *values, T *digits, size_t count,      \
+                                          void *stream) {                                                                             \
+        GadgetParams<T> g;                                                                                                            \
+        if (!make_gadget<T>(q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;                                                 \
+        if ((!values || !digits) && count) return PFHE_ERR_INVALID_ARG;                                                               \
+        PFHE_CUDA(launch_decompose<T>(g, values, digits, count, static_cast<cudaStream_t>(stream)));                                  \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_lift_small_batch(const T *moduli, size_t limbs, T small_modulus, const T *small, T *out, size_t count,  \
+                                               void *stream) {                                                                        \
+        if (!moduli || limbs == 0) return PFHE_ERR_RNS_EMPTY;                                                                         \
+        if (limbs > (size_t)kMaxLimbs || ((!small || !out) && count)) return PFHE_ERR_INVALID_ARG;                                    \
+        for (size_t i = 0; i < limbs; i++)                                                                                            \
+            if (moduli[i] <= small_modulus) return PFHE_ERR_INVALID_ARG;                                                              \
+        PFHE_CUDA(launch_rns_lift<T>(moduli, (int)limbs, small_modulus, small, out, count, static_cast<cudaStream_t>(stream)));       \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ggsw##B##_external_product_batch(const pfhe_ntt##B *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,       \
+                                                      const T *key, const T *in, T *out, size_t batch, int to_coeff, void *stream) {  \
+        return ext_prod<T>(t, k, log_basis, levels_in, key, in, out, batch, to_coeff, stream);                                        \
+    }                                                                                                                                 \
+    pfhe_status pfhe_blind_rotate##B##_batch(const pfhe_ntt##B *t, uint32_t log_basis, uint32_t levels_in, const T *bsk,              \
+                                             uint32_t n_lwe, const uint32_t *lwe, const T *test_vector, T *acc_out, size_t batch,     \
+                                             void *stream) {                                                                          \
+        return blind_rot<T>(t, log_basis, levels_in, bsk, n_lwe, lwe, test_vector, acc_out, batch, stream);                           \
+    }                                                                                                                                 \
+    pfhe_status pfhe_extract_lwe##B##_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, void *stream) {                       \
+        if ((!rlwe || !lwe) && batch) return PFHE_ERR_INVALID_ARG;                                                                    \
+        PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, static_cast<cudaStream_t>(stream)));                                  \
+        return PFHE_OK;                                                                                                               \
+    }
+
+PFHE_DEFINE_WORD(32, uint32_t)
+PFHE_DEFINE_WORD(64, uint64_t)
+
+pfhe_status pfhe_device_count(int *count) {
+    if (!count) return PFHE_ERR_INVALID_ARG;
+    PFHE_CUDA(cudaGetDeviceCount(count));
+    return PFHE_OK;
+}
+pfhe_status pfhe_malloc(int device, size_t bytes, void **dev_ptr) {
+    if (!dev_ptr) return PFHE_ERR_INVALID_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(cudaMalloc(dev_ptr, bytes));
+    return PFHE_OK;
+}
+pfhe_status pfhe_free(int device, void *dev_ptr) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(cudaFree(dev_ptr));
+    return PFHE_OK;
+}
+pfhe_status pfhe_memcpy_h2d(int device, void *dev_dst, const void *host_src, size_t bytes, void *stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+pfhe_status pfhe_memcpy_d2h(int device, void *host_dst, const void *dev_src, size_t bytes, void *stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+pfhe_status pfhe_stream_synchronize(int device, void *stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+pfhe_status pfhe_modmul_microbench(int device, int kind, uint32_t blocks, uint32_t iters, float *ms) {
+    if (!ms) return PFHE_ERR_INVALID_ARG;
+    DeviceGuard guard(device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(run_modmul_microbench(kind, blocks, iters, ms));
+    return PFHE_OK;
+}
+
+}  // extern "C"

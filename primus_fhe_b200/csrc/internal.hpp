@@ -1,0 +1,71 @@
+// internal.hpp -- C++ interface between the C-ABI layer (capi.cu) and the kernel translation units.
+#pragma once
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ntt_core.cuh"
+
+namespace pfhe {
+
+extern std::atomic<uint64_t> g_launches;  // every kernel launch issued by the library
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// LOGE of the register-pass kernel instantiated for (word bits, log_n); 0 = generic radix-2 kernel.
+int choose_loge(int bits, int log_n);
+
+// Gadget (ApproxSignedBasis) parameters, primus_decompose/src/primitive/basis.rs:47-176
+template <typename T> struct GadgetParams {
+    T q, basis_m1, q_minus_basis, carry_mask, threshold, add, init_mask;
+    uint32_t log_basis, levels, drop_bits;
+    uint32_t has_threshold, has_init_mask;
+};
+// returns false when (q, log_basis, levels_in) is rejected by the reference constructor's asserts
+template <typename T> bool make_gadget(T q, uint32_t log_basis, uint32_t levels_in, GadgetParams<T> &g);
+
+// ---- NTT family (ntt.cu) ------------------------------------------------------------------
+// polys are [batch*limbs][N]; polynomial p uses tables[p % limbs] (tb0 == tables[0] by value).
+template <typename T>
+cudaError_t launch_ntt(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys,
+                       bool forward, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_polymul(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c,
+                           size_t npolys, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_monomial(const DevNtt<T> &tb0, T coeff, const uint32_t *degrees, T *out, size_t batch, cudaStream_t stream);
+
+// ---- pointwise (pointwise.cu) -----------------------------------------------------------------
+struct SliceOpArgs {
+    int op;
+    int limbs;
+    size_t rows, n;
+};
+// per-limb constants passed in a small device-visible struct (<= 16 limbs)
+constexpr int kMaxLimbs = 16;
+template <typename T> struct LimbConsts {
+    Barrett<T> br[kMaxLimbs];
+    T scalar[kMaxLimbs], scalar_q[kMaxLimbs];
+};
+template <typename T>
+cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out,
+                            size_t rows, size_t n, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_decompose(const GadgetParams<T> &g, const T *values, T *digits, size_t count, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_rns_lift(const T *moduli_host, int limbs, T small_modulus, const T *small, T *out, size_t count,
+                            cudaStream_t stream);
+template <typename T>
+cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, cudaStream_t stream);
+
+// ---- lattice (lattice.cu) ---------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_external_product(const DevNtt<T> &tb, const GadgetParams<T> &g, uint32_t k, const T *key, const T *in,
+                                    T *out, size_t batch, bool to_coeff, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_blind_rotate(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe,
+                                const uint32_t *lwe, const T *test_vector, T *acc_out, size_t batch, cudaStream_t stream);
+
+cudaError_t run_modmul_microbench(int kind, uint32_t blocks, uint32_t iters, float *ms);
+
+}  // namespace pfhe

@@ -1,0 +1,338 @@
+// lattice.cu -- fused GGSW external product and blind rotation (single modulus, L = 1) for sm_100a.
+//
+// External product (per ciphertext, digits never leave the SM):
+//   out_c = [inv]( sum_{r<=k} sum_{l<levels} fwd(digit_l(in_r)) .* key[r][l][c] )
+// restating CrtGlwe::mul_dcrt_ggsw_to            primus_lattice/src/glwe/crt.rs:200-227
+//   -> add_dcrt_glev_mul_crt_poly_assign          primus_lattice/src/glwe/dcrt.rs:178-255
+//   -> add_dcrt_glwe_mul_dcrt_polynomial_assign   primus_lattice/src/glwe/dcrt.rs:108-126
+// with, for L = 1, the signed digits of ApproxSignedBasis (primus_decompose/src/primitive/basis.rs:254-283,
+// primitive/common.rs:246-259) == unsigned digit + centred lift (big_integer/common.rs:275-285 +
+// primus_rns/src/base.rs:721-731).  The key MAC accumulates double-word products lazily and reduces once
+// (reduce_dot_product, primus_modulus/src/common/compact/slice.rs:371-401; safe for <= 16 terms since
+// q < 2^(BITS-2)).
+//
+// Blind rotation (composed; not in the reference): the accumulator (2 polynomials)
+// stays in shared memory for all n_lwe CMux steps; only the LWE sample, the test vector and the final
+// accumulator touch HBM; the bootstrapping key streams through L2.
+#include "internal.hpp"
+
+namespace pfhe {
+
+struct LSyncBlock {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct LSyncWarp {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+template <int TPP> struct LSyncFor {
+    using type = LSyncBlock;
+};
+template <> struct LSyncFor<32> {
+    using type = LSyncWarp;
+};
+
+template <typename T> struct Wide2 {
+    T lo, hi;
+};
+__device__ __forceinline__ void mac_wide(uint64_t &acc, uint32_t a, uint32_t b) { acc += (uint64_t)a * b; }
+__device__ __forceinline__ void mac_wide(Wide2<uint64_t> &acc, uint64_t a, uint64_t b) {
+    const uint64_t lo = a * b, hi = __umul64hi(a, b);
+    acc.lo += lo;
+    acc.hi += hi + (acc.lo < lo);
+}
+template <typename T> struct AccOf;
+template <> struct AccOf<uint32_t> {
+    using type = uint64_t;
+    __device__ __forceinline__ static uint32_t reduce(const Barrett<uint32_t> &br, uint64_t a) {
+        return barrett_reduce_wide(br, (uint32_t)a, (uint32_t)(a >> 32));
+    }
+    __device__ __forceinline__ static void zero(uint64_t &a) { a = 0; }
+    __device__ __forceinline__ static void set(uint64_t &a, uint32_t v) { a = v; }
+};
+template <> struct AccOf<uint64_t> {
+    using type = Wide2<uint64_t>;
+    __device__ __forceinline__ static uint64_t reduce(const Barrett<uint64_t> &br, const Wide2<uint64_t> &a) {
+        return barrett_reduce_wide(br, a.lo, a.hi);
+    }
+    __device__ __forceinline__ static void zero(Wide2<uint64_t> &a) { a.lo = 0; a.hi = 0; }
+    __device__ __forceinline__ static void set(Wide2<uint64_t> &a, uint64_t v) { a.lo = v; a.hi = 0; }
+};
+
+// gadget digit of level `level` for value v (recomputes the carry chain from level 0; levels are few)
+template <typename T> __device__ __forceinline__ T gadget_digit(const GadgetParams<T> &g, T v, uint32_t level) {
+    if (g.has_threshold && v >= g.threshold) v += g.add;
+    uint32_t carry = g.has_init_mask ? (uint32_t)((v & g.init_mask) != 0) : 0u;
+    T d = 0;
+    for (uint32_t l = 0; l <= level; l++) {
+        const T t = ((v >> (g.drop_bits + l * g.log_basis)) & g.basis_m1) + carry;
+        carry = (t & g.carry_mask) != 0;
+        d = carry ? (t > g.basis_m1 ? T(0) : t + g.q_minus_basis) : t;
+    }
+    return d;
+}
+
+// Vec loads through the read-only path
+template <typename V> __device__ __forceinline__ V ldg_vec(const V *p) {
+    static_assert(sizeof(V) == 16, "16-byte vectors only");
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    V v;
+    *reinterpret_cast<uint4 *>(&v) = r;
+    return v;
+}
+
+template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
+    using Core = NttCore<T, LOGN, LOGE>;
+    using Acc = typename AccOf<T>::type;
+    static constexpr int N = Core::N, E = Core::E, TPP = Core::TPP, FB0 = Core::P::fb(0);
+    static constexpr int CW = Core::CW, NV = Core::NV;
+
+    // acc[c][j] (+)= sum_{r,l} fwd(digit_l(get(r, idx))) * key[r][l][c][t*E + j]
+    template <typename GetIn, typename SyncF>
+    __device__ __forceinline__ static void accumulate(GetIn get, const T *__restrict__ key, const GadgetParams<T> &g, const DevNtt<T> &tb,
+                                                      Acc (&acc)[COMPS][E], T *sm, int t, SyncF sync) {
+        const T q = tb.q, two_q = tb.two_q;
+        uint32_t terms = 0;
+#pragma unroll 1
+        for (int r = 0; r < COMPS; r++) {
+#pragma unroll 1
+            for (uint32_t l = 0; l < g.levels; l++) {
+                T x[E];
+#pragma unroll
+                for (int j = 0; j < E; j++) x[j] = gadget_digit<T>(g, get(r, Core::elem_index(FB0, t, j)), l);
+                Core::template fwd_from<0>(x, sm, tb, t, sync);
+#pragma unroll
+                for (int j = 0; j < E; j++) x[j] = csub(csub(x[j], two_q), q);
+                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+                if (terms == 16) {  // keep the lazy double-word sums below 2^(2*BITS)
+#pragma unroll
+                    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+                        for (int j = 0; j < E; j++) AccOf<T>::set(acc[c][j], AccOf<T>::reduce(tb.br, acc[c][j]));
+                    terms = 1;
+                }
+                terms++;
+#pragma unroll
+                for (int c = 0; c < COMPS; c++) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        const typename Core::Vec kv = ldg_vec(reinterpret_cast<const typename Core::Vec *>(kp + (size_t)c * N) + v);
+#pragma unroll
+                        for (int w = 0; w < CW; w++) mac_wide(acc[c][v * CW + w], x[v * CW + w], kv.v[w]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant__ GadgetParams<T> g, const T *__restrict__ key,
+                        const T *__restrict__ in, T *__restrict__ out, size_t batch, int to_coeff) {
+    using EP = ExtProd<T, LOGN, LOGE, COMPS>;
+    using Core = typename EP::Core;
+    constexpr int N = EP::N, E = EP::E, TPP = EP::TPP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    size_t ct = (size_t)blockIdx.x * PPB + grp;
+    const bool active = ct < batch;
+    if (!active) {
+        if (TPP == 32) return;
+        ct = batch - 1;
+    }
+    typename LSyncFor<TPP>::type sync;
+    const T *cin = in + ct * COMPS * N;
+    T *cout = out + ct * COMPS * N;
+    typename EP::Acc acc[COMPS][E];
+#pragma unroll
+    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+        for (int j = 0; j < E; j++) AccOf<T>::zero(acc[c][j]);
+    EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, acc, sm, t, sync);
+#pragma unroll
+    for (int c = 0; c < COMPS; c++) {
+        T x[E];
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
+        if (to_coeff) {
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < E; j++) cout[(size_t)c * N + Core::elem_index(EP::FB0, t, j)] = x[j];
+            }
+            sync();
+        } else {
+            if (active) Core::template sm_store<Core::P::NPASS - 1>(x, sm, t);
+            sync();
+            if (active) Core::copy_s2g(sm, cout + (size_t)c * N, t);
+            sync();
+        }
+    }
+}
+
+// Blind rotation: one ciphertext per thread group, accumulator resident in shared memory.
+template <typename T, int LOGN, int LOGE, int PPB>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant__ GadgetParams<T> g, const T *__restrict__ bsk,
+                    uint32_t n_lwe, const uint32_t *__restrict__ lwe, const T *__restrict__ test_vector, T *__restrict__ acc_out,
+                    size_t batch) {
+    using EP = ExtProd<T, LOGN, LOGE, 2>;
+    using Core = typename EP::Core;
+    constexpr int N = EP::N, E = EP::E, TPP = EP::TPP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * 3 * N;  // exchange buffer
+    T *accs = sm + N;                                               // ACC: [2][N], natural order
+    size_t ct = (size_t)blockIdx.x * PPB + grp;
+    const bool active = ct < batch;
+    if (!active) {
+        if (TPP == 32) return;
+        ct = batch - 1;
+    }
+    typename LSyncFor<TPP>::type sync;
+    const T q = tb.q;
+    const uint32_t *my_lwe = lwe + ct * (size_t)(n_lwe + 1);
+    const uint32_t two_n_mask = 2 * N - 1;
+    // ACC <- (0, tv * X^(2N - b))     (mul_monomial_assign, primus_poly/src/poly/mul.rs:74-99)
+    {
+        const uint32_t b = __ldg(my_lwe + n_lwe) & two_n_mask;
+        const uint32_t rot = (2 * N - b) & two_n_mask;
+        for (int i = t; i < N; i += TPP) {
+            accs[i] = 0;
+            // out[i] = sign * tv[(i - rot) mod 2N]
+            const uint32_t srcw = ((uint32_t)i - rot) & two_n_mask;
+            const T v = __ldg(test_vector + (srcw & (N - 1)));
+            accs[N + i] = (srcw >= (uint32_t)N) ? mod_neg<T>(v, q) : v;
+        }
+    }
+    sync();
+    const size_t rgsw_len = (size_t)2 * g.levels * 2 * N;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_lwe; i++) {
+        const uint32_t a = __ldg(my_lwe + i) & two_n_mask;
+        typename EP::Acc acc[2][E];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int j = 0; j < E; j++) AccOf<T>::zero(acc[c][j]);
+        // D = ACC * X^a - ACC, evaluated on the fly from the resident accumulator
+        auto getD = [&](int r, int idx) -> T {
+            const T *p = accs + r * N;
+            const uint32_t srcw = ((uint32_t)idx - a) & two_n_mask;
+            const T v = p[srcw & (N - 1)];
+            const T rotated = (srcw >= (uint32_t)N) ? mod_neg<T>(v, q) : v;
+            return mod_sub<T>(rotated, p[idx], q);
+        };
+        EP::accumulate(getD, bsk + (size_t)i * rgsw_len, g, tb, acc, sm, t, sync);
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            T x[E];
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
+            // ACC_c += result (each coefficient owned by exactly one thread)
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const int idx = Core::elem_index(EP::FB0, t, j);
+                accs[c * N + idx] = mod_add<T>(accs[c * N + idx], x[j], q);
+            }
+            sync();
+        }
+    }
+    if (active) {
+        T *o = acc_out + ct * 2 * N;
+        for (int i = t; i < 2 * N; i += TPP) o[i] = accs[i];
+    }
+}
+
+// ---- dispatch -------------------------------------------------------------------------------------
+template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
+static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
+                          cudaStream_t stream) {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
+    auto k = external_product_kernel<T, LOGN, LOGE, COMPS, PPB>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T, int LOGN, int LOGE, int PPB>
+static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe, const uint32_t *lwe,
+                          const T *tv, T *acc_out, size_t batch, cudaStream_t stream) {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    constexpr size_t smem = sizeof(T) * PPB * 3 * ((size_t)1 << LOGN);
+    auto k = blind_rotate_kernel<T, LOGN, LOGE, PPB>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// The lattice kernels use their own (smaller) register tile: DevNtt::fwd_pass/inv_pass must have been laid
+// out for lattice_loge(bits, log_n) -- capi.cu passes the matching DevNtt view.
+int lattice_loge(int bits, int log_n) {
+    if (log_n < 10 || log_n > 12) return 0;
+    return bits == 64 ? 3 : 4;
+}
+
+#define PFHE_EP_CASE(LOGN, LOGE, PPB)                                                                          \
+    case LOGN:                                                                                                  \
+        if (k == 1) return run_ep<T, LOGN, LOGE, 2, PPB>(tb, g, key, in, out, batch, to_coeff, s);              \
+        if (k == 2) return run_ep<T, LOGN, LOGE, 3, PPB>(tb, g, key, in, out, batch, to_coeff, s);              \
+        break;
+
+template <>
+cudaError_t launch_external_product<uint64_t>(const DevNtt<uint64_t> &tb, const GadgetParams<uint64_t> &g, uint32_t k, const uint64_t *key,
+                                              const uint64_t *in, uint64_t *out, size_t batch, bool to_coeff, cudaStream_t s) {
+    using T = uint64_t;
+    if (batch == 0) return cudaSuccess;
+    switch (tb.log_n) {
+        PFHE_EP_CASE(10, 3, 2)
+        PFHE_EP_CASE(11, 3, 1)
+        PFHE_EP_CASE(12, 3, 1)
+    }
+    return cudaErrorNotSupported;
+}
+template <>
+cudaError_t launch_external_product<uint32_t>(const DevNtt<uint32_t> &tb, const GadgetParams<uint32_t> &g, uint32_t k, const uint32_t *key,
+                                              const uint32_t *in, uint32_t *out, size_t batch, bool to_coeff, cudaStream_t s) {
+    using T = uint32_t;
+    if (batch == 0) return cudaSuccess;
+    switch (tb.log_n) {
+        PFHE_EP_CASE(10, 4, 2)
+        PFHE_EP_CASE(11, 4, 2)
+        PFHE_EP_CASE(12, 4, 1)
+    }
+    return cudaErrorNotSupported;
+}
+
+template <>
+cudaError_t launch_blind_rotate<uint64_t>(const DevNtt<uint64_t> &tb, const GadgetParams<uint64_t> &g, const uint64_t *bsk, uint32_t n_lwe,
+                                          const uint32_t *lwe, const uint64_t *tv, uint64_t *acc_out, size_t batch, cudaStream_t s) {
+    using T = uint64_t;
+    if (batch == 0) return cudaSuccess;
+    switch (tb.log_n) {
+        case 10: return run_br<T, 10, 3, 2>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 11: return run_br<T, 11, 3, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 12: return run_br<T, 12, 3, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+    }
+    return cudaErrorNotSupported;
+}
+template <>
+cudaError_t launch_blind_rotate<uint32_t>(const DevNtt<uint32_t> &tb, const GadgetParams<uint32_t> &g, const uint32_t *bsk, uint32_t n_lwe,
+                                          const uint32_t *lwe, const uint32_t *tv, uint32_t *acc_out, size_t batch, cudaStream_t s) {
+    using T = uint32_t;
+    if (batch == 0) return cudaSuccess;
+    switch (tb.log_n) {
+        case 10: return run_br<T, 10, 4, 2>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 11: return run_br<T, 11, 4, 2>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 12: return run_br<T, 12, 4, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+    }
+    return cudaErrorNotSupported;
+}
+
+}  // namespace pfhe

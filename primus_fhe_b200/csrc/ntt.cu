@@ -1,0 +1,404 @@
+// ntt.cu -- batched negacyclic NTT / INTT / fused polymul / monomial-NTT kernels for sm_100a.
+//
+// Replaces, for batches resident in HBM:
+//   NttTable::transform_slice / inverse_transform_slice   primus_ntt/src/ntt/prime64/table.rs:542-563
+//   (scalar semantics primus_ntt/src/ntt/prime64/scalar/transform.rs:13-320, prime32/scalar/transform.rs:13-273)
+//   DcrtTable::transform_slice (per-limb loop)            primus_ntt/src/dcrt/prime64.rs:106-111
+//   monomial transforms                                   primus_ntt/src/ntt/prime64/table.rs:565-651
+//   transform + NttPolynomial::mul_assign + inverse       primus_lattice/src/rlwe/coeff.rs:92-122
+//
+// One polynomial per thread group (TPP threads); a CTA carries PPB groups. Each polynomial is read from
+// HBM once and written once; everything in between lives in registers / shared memory.
+#include "internal.hpp"
+#include "host_math.hpp"
+
+namespace pfhe {
+
+std::atomic<uint64_t> g_launches{0};
+
+int choose_loge(int bits, int log_n) {
+    if (bits == 64) {
+        switch (log_n) {
+            case 10: return 5;
+            case 11: return 4;
+            case 12: return 4;
+            case 13: return 5;
+            case 14: return 5;
+            default: return 0;
+        }
+    }
+    switch (log_n) {
+        case 10: return 5;
+        case 11: return 6;
+        case 12: return 6;
+        case 13: return 5;
+        case 14: return 5;
+        case 15: return 5;
+        default: return 0;
+    }
+}
+
+struct SyncBlock {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct SyncWarp {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+template <int TPP> struct SyncFor {
+    using type = SyncBlock;
+};
+template <> struct SyncFor<32> {
+    using type = SyncWarp;
+};
+
+template <typename T> __device__ __forceinline__ DevNtt<T> pick_table(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, size_t poly) {
+    if (limbs <= 1) return tb0;
+    return tables[poly % (size_t)limbs];
+}
+
+// ------------------------------------------------------------------------------------------------
+// register-pass kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T, int LOGN, int LOGE, int PPB, bool FWD>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+ntt_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *__restrict__ src,
+           T *__restrict__ dst, size_t npolys) {
+    using Core = NttCore<T, LOGN, LOGE>;
+    constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    size_t poly = (size_t)blockIdx.x * PPB + grp;
+    const bool active = poly < npolys;
+    if (!active) {
+        if (TPP == 32) return;  // warp-private group: nothing to synchronise with
+        poly = npolys - 1;
+    }
+    const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    const T *g_in = src + poly * N;
+    T *g_out = dst + poly * N;
+    typename SyncFor<TPP>::type sync;
+    T x[E];
+    if (FWD) {
+        Core::forward_g2r(g_in, x, sm, tb, t, sync);
+        if (active) Core::sm_store<Core::P::NPASS - 1>(x, sm, t);
+        sync();
+        if (active) Core::copy_s2g(sm, g_out, t);
+    } else {
+        Core::load_g2r(g_in, x, sm, t, sync);
+        Core::inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
+        if (active) {
+            constexpr int FB0 = Core::P::fb(0);
+#pragma unroll
+            for (int j = 0; j < E; j++) g_out[Core::elem_index(FB0, t, j)] = x[j];
+        }
+    }
+}
+
+template <typename T, int LOGN, int LOGE, int PPB>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+polymul_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *__restrict__ a,
+               const T *__restrict__ b, T *__restrict__ c, size_t npolys) {
+    using Core = NttCore<T, LOGN, LOGE>;
+    constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    size_t poly = (size_t)blockIdx.x * PPB + grp;
+    const bool active = poly < npolys;
+    if (!active) {
+        if (TPP == 32) return;
+        poly = npolys - 1;
+    }
+    const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    typename SyncFor<TPP>::type sync;
+    T xa[E], xb[E];
+    Core::forward_g2r(a + poly * N, xa, sm, tb, t, sync);
+    Core::forward_g2r(b + poly * N, xb, sm, tb, t, sync);
+    // pointwise product, exact mod q (BarrettModulus::reduce_mul, primus_modulus/src/barrett/ops.rs:276-283)
+#pragma unroll
+    for (int j = 0; j < E; j++) xa[j] = barrett_mul<T>(tb.br, xa[j], xb[j]);
+    Core::inv_from<Core::P::NPASS - 1>(xa, sm, tb, t, sync);
+    if (active) {
+        constexpr int FB0 = Core::P::fb(0);
+        T *g_out = c + poly * N;
+#pragma unroll
+        for (int j = 0; j < E; j++) g_out[Core::elem_index(FB0, t, j)] = xa[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic radix-2 kernel: any 1 <= log_n that fits shared memory (sizes without a register-pass
+// instantiation, e.g. the reference's small round-trip tests N = 8..512)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void ntt_generic_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs,
+                                   const T *__restrict__ src, T *__restrict__ dst, size_t npolys, int forward) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const size_t poly = blockIdx.x;
+    const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    const int logn = tb.log_n, n = 1 << logn, half = n >> 1;
+    const T q = tb.q, two_q = tb.two_q;
+    const T *g_in = src + poly * n;
+    T *g_out = dst + poly * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm[i] = g_in[i];
+    __syncthreads();
+    if (forward) {
+        for (int s = 0; s < logn; s++) {
+            const int lg = logn - 1 - s, gap = 1 << lg;
+            for (int bidx = threadIdx.x; bidx < half; bidx += blockDim.x) {
+                const int blk = bidx >> lg, j = bidx & (gap - 1), i0 = (blk << (lg + 1)) | j;
+                const auto w = ld_pair<T>(tb.fwd + ((1 << s) + blk));
+                T x = sm[i0], y = sm[i0 + gap];
+                fwd_bfly<T>(x, y, w.x, w.y, q, two_q);
+                sm[i0] = x;
+                sm[i0 + gap] = y;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g_out[i] = csub(csub(sm[i], two_q), q);
+    } else {
+        for (int lg = 0; lg < logn; lg++) {
+            const int gap = 1 << lg, base = 1 + n - (n >> lg);
+            for (int bidx = threadIdx.x; bidx < half; bidx += blockDim.x) {
+                const int blk = bidx >> lg, j = bidx & (gap - 1), i0 = (blk << (lg + 1)) | j;
+                const auto w = ld_pair<T>(tb.inv + (base + blk));
+                T x = sm[i0], y = sm[i0 + gap];
+                if (lg == logn - 1) {
+                    T tx = x + y, ty = x + two_q - y;
+                    x = shoup<T>(tx, tb.inv_n, tb.inv_n_q, q);
+                    y = shoup<T>(ty, w.x, w.y, q);
+                } else {
+                    inv_bfly<T>(x, y, w.x, w.y, q, two_q);
+                }
+                sm[i0] = x;
+                sm[i0 + gap] = y;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g_out[i] = sm[i];
+    }
+}
+
+template <typename T>
+__global__ void polymul_generic_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs,
+                                       const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t npolys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t poly = blockIdx.x;
+    const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    const int logn = tb.log_n, n = 1 << logn, half = n >> 1;
+    T *sa = reinterpret_cast<T *>(smem_raw), *sb = sa + n;
+    const T q = tb.q, two_q = tb.two_q;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sa[i] = a[poly * n + i];
+        sb[i] = b[poly * n + i];
+    }
+    __syncthreads();
+    for (int s = 0; s < logn; s++) {
+        const int lg = logn - 1 - s, gap = 1 << lg;
+        for (int bidx = threadIdx.x; bidx < half; bidx += blockDim.x) {
+            const int blk = bidx >> lg, j = bidx & (gap - 1), i0 = (blk << (lg + 1)) | j;
+            const auto w = ld_pair<T>(tb.fwd + ((1 << s) + blk));
+            fwd_bfly<T>(sa[i0], sa[i0 + gap], w.x, w.y, q, two_q);
+            fwd_bfly<T>(sb[i0], sb[i0 + gap], w.x, w.y, q, two_q);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T x = csub(csub(sa[i], two_q), q), y = csub(csub(sb[i], two_q), q);
+        sa[i] = barrett_mul<T>(tb.br, x, y);
+    }
+    __syncthreads();
+    for (int lg = 0; lg < logn; lg++) {
+        const int gap = 1 << lg, base = 1 + n - (n >> lg);
+        for (int bidx = threadIdx.x; bidx < half; bidx += blockDim.x) {
+            const int blk = bidx >> lg, j = bidx & (gap - 1), i0 = (blk << (lg + 1)) | j;
+            const auto w = ld_pair<T>(tb.inv + (base + blk));
+            T x = sa[i0], y = sa[i0 + gap];
+            if (lg == logn - 1) {
+                T tx = x + y, ty = x + two_q - y;
+                x = shoup<T>(tx, tb.inv_n, tb.inv_n_q, q);
+                y = shoup<T>(ty, w.x, w.y, q);
+            } else {
+                inv_bfly<T>(x, y, w.x, w.y, q, two_q);
+            }
+            sa[i0] = x;
+            sa[i0 + gap] = y;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c[poly * n + i] = sa[i];
+}
+
+// NTT(coeff * X^degree)[i] = coeff * psi^(((2 brv(i)+1) degree) mod 2N)   (table.rs:565-609)
+template <typename T>
+__global__ void monomial_kernel(const __grid_constant__ DevNtt<T> tb, T coeff, T coeff_q, const uint32_t *__restrict__ degrees,
+                                T *__restrict__ out, size_t batch) {
+    const int logn = tb.log_n, n = 1 << logn;
+    const size_t total = batch * (size_t)n;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t bidx = gid >> logn;
+        const uint32_t i = (uint32_t)(gid & (n - 1));
+        const uint32_t deg = degrees[bidx] & (2 * n - 1);
+        T v;
+        if (coeff == 0) {
+            v = 0;
+        } else {
+            const uint32_t r = __brev(i) >> (32 - logn);
+            const uint32_t e = ((2 * r + 1) * deg) & (2 * n - 1);
+            const T w = tb.ordinal[e];
+            v = (coeff == 1) ? w : shoup<T>(w, coeff, coeff_q, tb.q);
+        }
+        out[gid] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+template <typename T, int LOGN, int LOGE, int PPB>
+static cudaError_t run_ntt(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys, bool fwd,
+                           cudaStream_t stream) {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
+    const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
+    cudaError_t e;
+    if (fwd) {
+        auto k = ntt_kernel<T, LOGN, LOGE, PPB, true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
+    } else {
+        auto k = ntt_kernel<T, LOGN, LOGE, PPB, false>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T, int LOGN, int LOGE, int PPB>
+static cudaError_t run_polymul(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c, size_t npolys,
+                               cudaStream_t stream) {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
+    const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
+    auto k = polymul_kernel<T, LOGN, LOGE, PPB>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T> static int generic_threads(int log_n) {
+    int half = 1 << (log_n - 1);
+    int th = half < 32 ? 32 : half;
+    return th > 512 ? 512 : th;
+}
+
+template <typename T>
+static cudaError_t run_generic(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys, bool fwd,
+                               cudaStream_t stream) {
+    const size_t smem = sizeof(T) << tb0.log_n;
+    auto k = ntt_generic_kernel<T>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)npolys, generic_threads<T>(tb0.log_n), smem, stream>>>(tb0, tables, limbs, src, dst, npolys, fwd ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, const uint64_t *src,
+                                 uint64_t *dst, size_t npolys, bool fwd, cudaStream_t s) {
+    using T = uint64_t;
+    if (npolys == 0) return cudaSuccess;
+    if (tb0.loge != 0) {
+        switch (tb0.log_n) {
+            case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 11: return run_ntt<T, 11, 4, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 12: return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 13: return run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 14: return run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+        }
+    }
+    return run_generic<T>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+}
+template <>
+cudaError_t launch_ntt<uint32_t>(const DevNtt<uint32_t> &tb0, const DevNtt<uint32_t> *tables, int limbs, const uint32_t *src,
+                                 uint32_t *dst, size_t npolys, bool fwd, cudaStream_t s) {
+    using T = uint32_t;
+    if (npolys == 0) return cudaSuccess;
+    if (tb0.loge != 0) {
+        switch (tb0.log_n) {
+            case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 11: return run_ntt<T, 11, 6, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 12: return run_ntt<T, 12, 6, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 13: return run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 14: return run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 15: return run_ntt<T, 15, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+        }
+    }
+    return run_generic<T>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+}
+
+template <typename T>
+static cudaError_t run_polymul_generic(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c,
+                                       size_t npolys, cudaStream_t stream) {
+    const size_t smem = 2 * (sizeof(T) << tb0.log_n);
+    auto k = polymul_generic_kernel<T>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)npolys, generic_threads<T>(tb0.log_n), smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_polymul<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, const uint64_t *a,
+                                     const uint64_t *b, uint64_t *c, size_t npolys, cudaStream_t s) {
+    using T = uint64_t;
+    if (npolys == 0) return cudaSuccess;
+    if (tb0.loge != 0) {
+        switch (tb0.log_n) {
+            case 10: return run_polymul<T, 10, 5, 4>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 11: return run_polymul<T, 11, 4, 2>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 12: return run_polymul<T, 12, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 13: return run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 14: return run_polymul<T, 14, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+        }
+    }
+    return run_polymul_generic<T>(tb0, tables, limbs, a, b, c, npolys, s);
+}
+template <>
+cudaError_t launch_polymul<uint32_t>(const DevNtt<uint32_t> &tb0, const DevNtt<uint32_t> *tables, int limbs, const uint32_t *a,
+                                     const uint32_t *b, uint32_t *c, size_t npolys, cudaStream_t s) {
+    using T = uint32_t;
+    if (npolys == 0) return cudaSuccess;
+    if (tb0.loge != 0) {
+        switch (tb0.log_n) {
+            case 10: return run_polymul<T, 10, 5, 4>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 11: return run_polymul<T, 11, 6, 4>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 12: return run_polymul<T, 12, 6, 2>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 13: return run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 14: return run_polymul<T, 14, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 15: return run_polymul<T, 15, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+        }
+    }
+    return run_polymul_generic<T>(tb0, tables, limbs, a, b, c, npolys, s);
+}
+
+template <typename T>
+cudaError_t launch_monomial(const DevNtt<T> &tb0, T coeff, const uint32_t *degrees, T *out, size_t batch, cudaStream_t stream) {
+    if (batch == 0) return cudaSuccess;
+    const size_t total = batch << tb0.log_n;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    const T cq = coeff ? host::shoup_quot<T>(coeff, tb0.q) : 0;
+    monomial_kernel<T><<<grid, 256, 0, stream>>>(tb0, coeff, cq, degrees, out, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_monomial<uint32_t>(const DevNtt<uint32_t> &, uint32_t, const uint32_t *, uint32_t *, size_t, cudaStream_t);
+template cudaError_t launch_monomial<uint64_t>(const DevNtt<uint64_t> &, uint64_t, const uint32_t *, uint64_t *, size_t, cudaStream_t);
+
+}  // namespace pfhe

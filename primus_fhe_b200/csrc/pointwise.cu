@@ -1,0 +1,307 @@
+// pointwise.cu -- HBM-streaming element-wise kernels: modular slice operators, gadget decomposition,
+// RNS centred lift, LWE sample extraction, and the integer-pipe microbenchmark.
+//
+// Replaces:
+//   ReduceMulSlice / ReduceMulAddSlice / Reduce{Add,Sub,Neg}Slice     primus_reduce/src/slice_ops.rs:43-230
+//     (bodies primus_modulus/src/common/compact/slice.rs:106-365, Barrett primus_modulus/src/barrett/ops.rs:276-322)
+//   FactorSliceOps with a ShoupFactor                                  primus_factor/src/ops.rs:58-118, common/slice.rs:7-107
+//   per-limb DcrtPolynomial mul / add_mul / factor ops                 primus_poly/src/dcrt/mul.rs:142-187, dcrt/mod.rs:105-123
+//   ApproxSignedBasis init + OnceSignedDecomposer levels              primus_decompose/src/primitive/basis.rs:254-406, common.rs:219-273
+//   RNSBase::wrapping_decompose_small_values_to                        primus_rns/src/base.rs:279-315, :721-731
+//   Rlwe::extract_lwe                                                  primus_lattice/src/rlwe/coeff.rs:264-288
+// All kernels are pure streaming: 128-bit vector accesses, grid sized in multiples of the SM count.
+#include "internal.hpp"
+#include "host_math.hpp"
+#include "pfhe.h"
+
+namespace pfhe {
+
+constexpr int kSMs = 148;
+
+template <typename T> struct VecOf {
+    static constexpr int W = 16 / sizeof(T);
+    struct alignas(16) type {
+        T v[W];
+    };
+};
+
+template <typename T, int OP>
+__device__ __forceinline__ T apply_op(const Barrett<T> &br, T s, T sq, T a, T b, T c, T o) {
+    const T q = br.q;
+    switch (OP) {
+        case PFHE_OP_MUL: return barrett_mul<T>(br, a, b);
+        case PFHE_OP_ADD_MUL: return barrett_mul_add<T>(br, a, b, o);
+        case PFHE_OP_SUB_MUL: return mod_sub<T>(o, barrett_mul<T>(br, a, b), q);
+        case PFHE_OP_MUL_ADD: return barrett_mul_add<T>(br, a, b, c);
+        case PFHE_OP_ADD: return mod_add<T>(a, b, q);
+        case PFHE_OP_SUB: return mod_sub<T>(a, b, q);
+        case PFHE_OP_NEG: return mod_neg<T>(a, q);
+        case PFHE_OP_MUL_SCALAR: return barrett_mul<T>(br, a, s);
+        case PFHE_OP_ADD_MUL_SCALAR: return barrett_mul_add<T>(br, a, s, o);
+        case PFHE_OP_FACTOR_MUL: return shoup<T>(a, s, sq, q);
+        case PFHE_OP_ADD_FACTOR_MUL: return mod_add<T>(o, shoup<T>(a, s, sq, q), q);
+        case PFHE_OP_SUB_FACTOR_MUL: return mod_sub<T>(o, shoup<T>(a, s, sq, q), q);
+    }
+    return 0;
+}
+
+constexpr bool op_reads_b(int op) { return op == PFHE_OP_MUL || op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_MUL_ADD || op == PFHE_OP_ADD || op == PFHE_OP_SUB; }
+constexpr bool op_reads_c(int op) { return op == PFHE_OP_MUL_ADD; }
+constexpr bool op_reads_out(int op) { return op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_ADD_FACTOR_MUL || op == PFHE_OP_SUB_FACTOR_MUL; }
+
+// slices are [rows][limbs][n]; vectorised when n % W == 0 (always true for polynomial lengths >= 4)
+template <typename T, int OP, bool VEC>
+__global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, const T *__restrict__ a,
+                                                       const T *__restrict__ b, const T *__restrict__ c, T *out, size_t rows, size_t n) {
+    constexpr int W = VEC ? VecOf<T>::W : 1;
+    using V = typename VecOf<T>::type;
+    const size_t per_row = n / W, total = rows * (size_t)limbs * per_row;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const int limb = limbs == 1 ? 0 : (int)((gid / per_row) % (size_t)limbs);
+        const Barrett<T> br = lc.br[limb];
+        const T s = lc.scalar[limb], sq = lc.scalar_q[limb];
+        if (VEC) {
+            V va = reinterpret_cast<const V *>(a)[gid], vb, vc, vo;
+            if (op_reads_b(OP)) vb = reinterpret_cast<const V *>(b)[gid];
+            if (op_reads_c(OP)) vc = reinterpret_cast<const V *>(c)[gid];
+            if (op_reads_out(OP)) vo = reinterpret_cast<const V *>(out)[gid];
+#pragma unroll
+            for (int k = 0; k < W; k++)
+                vo.v[k] = apply_op<T, OP>(br, s, sq, va.v[k], op_reads_b(OP) ? vb.v[k] : T(0), op_reads_c(OP) ? vc.v[k] : T(0),
+                                          op_reads_out(OP) ? vo.v[k] : T(0));
+            reinterpret_cast<V *>(out)[gid] = vo;
+        } else {
+            out[gid] = apply_op<T, OP>(br, s, sq, a[gid], op_reads_b(OP) ? b[gid] : T(0), op_reads_c(OP) ? c[gid] : T(0),
+                                       op_reads_out(OP) ? out[gid] : T(0));
+        }
+    }
+}
+
+static unsigned stream_grid(size_t work_items, int threads) {
+    size_t blocks = (work_items + threads - 1) / threads;
+    const size_t cap = (size_t)kSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (unsigned)blocks;
+}
+
+template <typename T, int OP>
+static cudaError_t run_slice_op(const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out, size_t rows, size_t n,
+                                cudaStream_t stream) {
+    constexpr int W = VecOf<T>::W;
+    auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = (n % W == 0) && aligned(a) && aligned(out) && (!b || aligned(b)) && (!c || aligned(c));
+    const size_t total = rows * (size_t)limbs * (vec ? n / W : n);
+    if (total == 0) return cudaSuccess;
+    if (vec)
+        slice_op_kernel<T, OP, true><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n);
+    else
+        slice_op_kernel<T, OP, false><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out, size_t rows, size_t n,
+                            cudaStream_t s) {
+    switch (op) {
+#define PFHE_CASE(OPC) \
+    case OPC: return run_slice_op<T, OPC>(lc, limbs, a, b, c, out, rows, n, s);
+        PFHE_CASE(PFHE_OP_MUL)
+        PFHE_CASE(PFHE_OP_ADD_MUL)
+        PFHE_CASE(PFHE_OP_SUB_MUL)
+        PFHE_CASE(PFHE_OP_MUL_ADD)
+        PFHE_CASE(PFHE_OP_ADD)
+        PFHE_CASE(PFHE_OP_SUB)
+        PFHE_CASE(PFHE_OP_NEG)
+        PFHE_CASE(PFHE_OP_MUL_SCALAR)
+        PFHE_CASE(PFHE_OP_ADD_MUL_SCALAR)
+        PFHE_CASE(PFHE_OP_FACTOR_MUL)
+        PFHE_CASE(PFHE_OP_ADD_FACTOR_MUL)
+        PFHE_CASE(PFHE_OP_SUB_FACTOR_MUL)
+#undef PFHE_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+template cudaError_t launch_slice_op<uint32_t>(int, const LimbConsts<uint32_t> &, int, const uint32_t *, const uint32_t *, const uint32_t *,
+                                               uint32_t *, size_t, size_t, cudaStream_t);
+template cudaError_t launch_slice_op<uint64_t>(int, const LimbConsts<uint64_t> &, int, const uint64_t *, const uint64_t *, const uint64_t *,
+                                               uint64_t *, size_t, size_t, cudaStream_t);
+
+// ---- gadget parameters (host) ---------------------------------------------------------------------
+template <typename T> bool make_gadget(T q, uint32_t log_basis, uint32_t levels_in, GadgetParams<T> &g) {
+    constexpr int BITS = sizeof(T) * 8;
+    if (log_basis == 0 || (int)log_basis >= BITS) return false;
+    if (q < 3 || (q & (q - 1)) == 0) return false;  // NTT primes only (power-of-two moduli are the torus side)
+    const uint32_t value_bits = (uint32_t)host::bit_length<T>(q);
+    if (value_bits < log_basis) return false;
+    uint32_t levels = value_bits / log_basis, drop = value_bits - levels * log_basis;
+    if (levels_in) {
+        if (levels < levels_in) return false;
+        levels = levels_in;
+        drop = value_bits - levels * log_basis;
+    }
+    if (levels == 0) return false;
+    g.q = q;
+    g.log_basis = log_basis;
+    g.levels = levels;
+    g.drop_bits = drop;
+    const T basis = (T)1 << log_basis;
+    g.basis_m1 = basis - 1;
+    g.q_minus_basis = q - basis;
+    g.carry_mask = log_basis == 1 ? (T)2 : (T)(basis | (basis >> 1));
+    g.has_init_mask = drop > 0;
+    g.init_mask = drop > 0 ? (T)1 << (drop - 1) : 0;
+    T value = 0;
+    bool have = false;
+    if (log_basis == 1) {
+        if (drop != 0) {
+            for (uint32_t i = 0; i < levels; i++) value = (T)((value << 1) | 1);
+            value = (T)((value << 1) | 1);
+            value = (T)(value << (drop - 1));
+            have = value < q;
+        }
+    } else {
+        for (uint32_t i = 0; i < levels; i++) value = (T)((value << log_basis) | (g.basis_m1 >> 1));
+        if (drop > 0) {
+            value = (T)((value << 1) | 1);
+            value = (T)(value << (drop - 1));
+        } else {
+            value = (T)(value + 1);
+        }
+        have = value < q;
+    }
+    g.has_threshold = have;
+    g.threshold = value;
+    const T all = value_bits == (uint32_t)BITS ? (T)~(T)0 : (T)(((T)1 << value_bits) - 1);
+    g.add = (T)(all - (q - 1));
+    return true;
+}
+template bool make_gadget<uint32_t>(uint32_t, uint32_t, uint32_t, GadgetParams<uint32_t> &);
+template bool make_gadget<uint64_t>(uint64_t, uint32_t, uint32_t, GadgetParams<uint64_t> &);
+
+// digits[l][i], LSB level first; each digit canonical mod q
+template <typename T>
+__global__ void __launch_bounds__(256) decompose_kernel(const __grid_constant__ GadgetParams<T> g, const T *__restrict__ values,
+                                                        T *__restrict__ digits, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        T v = values[i];
+        if (g.has_threshold && v >= g.threshold) v += g.add;
+        uint32_t carry = g.has_init_mask ? (uint32_t)((v & g.init_mask) != 0) : 0u;
+        for (uint32_t l = 0; l < g.levels; l++) {
+            T t = ((v >> (g.drop_bits + l * g.log_basis)) & g.basis_m1) + carry;
+            carry = (t & g.carry_mask) != 0;
+            T d = carry ? (t > g.basis_m1 ? T(0) : t + g.q_minus_basis) : t;
+            digits[(size_t)l * count + i] = d;
+        }
+    }
+}
+template <typename T> cudaError_t launch_decompose(const GadgetParams<T> &g, const T *values, T *digits, size_t count, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    decompose_kernel<T><<<stream_grid(count, 256), 256, 0, stream>>>(g, values, digits, count);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_decompose<uint32_t>(const GadgetParams<uint32_t> &, const uint32_t *, uint32_t *, size_t, cudaStream_t);
+template cudaError_t launch_decompose<uint64_t>(const GadgetParams<uint64_t> &, const uint64_t *, uint64_t *, size_t, cudaStream_t);
+
+template <typename T> struct LiftConsts {
+    T temp[kMaxLimbs];  // q_i - small_modulus
+    T half;
+    int limbs, unsigned_mode;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) rns_lift_kernel(const __grid_constant__ LiftConsts<T> lc, const T *__restrict__ small,
+                                                       T *__restrict__ out, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const T v = small[i];
+        for (int l = 0; l < lc.limbs; l++) out[(size_t)l * count + i] = (lc.unsigned_mode || v < lc.half) ? v : lc.temp[l] + v;
+    }
+}
+template <typename T>
+cudaError_t launch_rns_lift(const T *moduli_host, int limbs, T small_modulus, const T *small, T *out, size_t count, cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    LiftConsts<T> lc;
+    lc.limbs = limbs;
+    lc.unsigned_mode = small_modulus == 2;
+    lc.half = (T)((small_modulus + 1) / 2);
+    for (int l = 0; l < limbs; l++) lc.temp[l] = moduli_host[l] - small_modulus;
+    rns_lift_kernel<T><<<stream_grid(count, 256), 256, 0, stream>>>(lc, small, out, count);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_rns_lift<uint32_t>(const uint32_t *, int, uint32_t, const uint32_t *, uint32_t *, size_t, cudaStream_t);
+template cudaError_t launch_rns_lift<uint64_t>(const uint64_t *, int, uint64_t, const uint64_t *, uint64_t *, size_t, cudaStream_t);
+
+// lwe = [a_0, -a_{N-1}, ..., -a_1, b_0]
+template <typename T>
+__global__ void __launch_bounds__(256) extract_lwe_kernel(T q, const T *__restrict__ rlwe, T *__restrict__ lwe, size_t n, size_t batch) {
+    const size_t per = n + 1, total = batch * per;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t bidx = gid / per, i = gid % per;
+        const T *src = rlwe + bidx * 2 * n;
+        T v;
+        if (i == 0) v = src[0];
+        else if (i == n) v = src[n];
+        else v = mod_neg<T>(src[n - i], q);
+        lwe[gid] = v;
+    }
+}
+template <typename T> cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, cudaStream_t stream) {
+    if (batch == 0) return cudaSuccess;
+    extract_lwe_kernel<T><<<stream_grid(batch * (n + 1), 256), 256, 0, stream>>>(q, rlwe, lwe, n, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_extract_lwe<uint32_t>(uint32_t, const uint32_t *, uint32_t *, size_t, size_t, cudaStream_t);
+template cudaError_t launch_extract_lwe<uint64_t>(uint64_t, const uint64_t *, uint64_t *, size_t, size_t, cudaStream_t);
+
+// ---- integer-pipe microbenchmark --------------------------------------------------------------------
+// 8 independent chains of Harvey butterflies per thread, registers only: measures the achievable
+// butterfly rate (the "modmul ops at integer-pipe peak" roofline denominator).
+template <typename T> __global__ void __launch_bounds__(256) modmul_bench_kernel(T q, T w, T wq, uint32_t iters, T *sink) {
+    T x[8], y[8];
+    const T two_q = q * 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x[k] = (T)(threadIdx.x * 7 + k + blockIdx.x) % q;
+        y[k] = (T)(threadIdx.x * 13 + 5 * k + 1) % q;
+    }
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) fwd_bfly<T>(x[k], y[k], w, wq, q, two_q);
+    }
+    T acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc ^= x[k] ^ y[k];
+    if (acc == (T)0x1234567) sink[0] = acc;
+}
+
+cudaError_t run_modmul_microbench(int kind, uint32_t blocks, uint32_t iters, float *ms) {
+    cudaEvent_t e0, e1;
+    cudaError_t e;
+    if ((e = cudaEventCreate(&e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&e1)) != cudaSuccess) return e;
+    void *sink = nullptr;
+    if ((e = cudaMalloc(&sink, 64)) != cudaSuccess) return e;
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        if (kind == 0) {
+            const uint32_t q = 132120577u, w = 73993u;
+            modmul_bench_kernel<uint32_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint32_t>(w, q), iters, (uint32_t *)sink);
+        } else {
+            const uint64_t q = 1125899906826241ull, w = 46909545429ull;
+            modmul_bench_kernel<uint64_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint64_t>(w, q), iters, (uint64_t *)sink);
+        }
+        count_launch();
+        cudaEventRecord(e1);
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        cudaEventElapsedTime(ms, e0, e1);
+    }
+    cudaFree(sink);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return e;
+}
+
+}  // namespace pfhe

@@ -1,0 +1,138 @@
+"""GPU parity for the pointwise slice operators, gadget decomposition, RNS lift and LWE extraction.
+
+Mirrors primus_modulus/tests/barrett_modulus.rs:25-303 (slice ops vs a second implementation, odd
+lengths 0..65 for vector tails), primus_factor/tests/shoup_factor.rs:19-165 (Shoup == Barrett),
+primus_decompose/tests/non_pow_of_2.rs:13-232 (slice == scalar, digits), primus_rns/tests/rns.rs (lift rule).
+"""
+import numpy as np
+import pytest
+
+from conftest import Q27, Q50, Q50B, Q60
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+    import torch
+    return torch.from_numpy(x.view(np.int64 if x.dtype == np.uint64 else np.int32)).cuda()
+
+
+def _host(t, dt):
+    return t.cpu().numpy().view(dt)
+
+
+@pytest.mark.parametrize("bits,q", [(64, Q50), (64, Q60), (32, Q27), (32, 1073692673), (64, 3), (32, 7)])
+@pytest.mark.parametrize("n", [0, 1, 3, 17, 64, 65, 4096, 100003])
+def test_slice_ops_match_oracle(bits, q, n):
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(n + bits)
+    a, b, c = (rng.integers(0, q, n, dtype=np.uint64).astype(dt) for _ in range(3))
+    if n > 2:
+        a[0], b[0], c[0] = q - 1, q - 1, q - 1
+        a[1], b[1] = 0, q - 1
+    s = int(rng.integers(0, q))
+    om, gm = O.BarrettModulus(q, bits), P.BarrettModulus(q, bits)
+    of = O.ShoupFactor(s, q, bits)
+    if n == 0:
+        return
+    da, db, dc = _dev(a), _dev(b), _dev(c)
+    out = _dev(np.zeros(n, dtype=dt))
+    assert np.array_equal(_host(gm.reduce_mul_slice_to(da, db, out), dt), om.reduce_mul_slice_to(a, b))
+    assert np.array_equal(_host(gm.reduce_mul_add_slice_to(da, db, dc, out), dt), om.reduce_mul_add_slice_to(a, b, c))
+    assert np.array_equal(_host(gm.reduce_add_slice_to(da, db, out), dt), om.reduce_add_slice_to(a, b))
+    assert np.array_equal(_host(gm.reduce_sub_slice_to(da, db, out), dt), om.reduce_sub_slice_to(a, b))
+    assert np.array_equal(_host(gm.reduce_neg_slice_to(da, out), dt), om.reduce_neg_slice_to(a))
+    assert np.array_equal(_host(gm.reduce_mul_scalar_slice_to(da, s, out), dt), om.reduce_mul_scalar_slice_to(a, s))
+    acc = _dev(c.copy()); gm.reduce_add_mul_slice_assign(acc, da, db)
+    assert np.array_equal(_host(acc, dt), om.reduce_add_mul_slice_assign(c.copy(), a, b))
+    acc = _dev(c.copy()); gm.reduce_sub_mul_slice_assign(acc, da, db)
+    assert np.array_equal(_host(acc, dt), om.reduce_sub_mul_slice_assign(c.copy(), a, b))
+    acc = _dev(c.copy()); gm.reduce_add_mul_scalar_slice_assign(acc, da, s)
+    assert np.array_equal(_host(acc, dt), om.reduce_add_mul_scalar_slice_assign(c.copy(), a, s))
+    # Shoup factor ops == Barrett (shoup_factor.rs:19-60)
+    assert np.array_equal(_host(gm.factor_mul_slice_to(s, da, out), dt), of.factor_mul_slice_to(a))
+    assert np.array_equal(of.factor_mul_slice_to(a), om.reduce_mul_scalar_slice_to(a, s))
+    acc = _dev(c.copy()); gm.add_factor_mul_slice_assign(s, acc, da)
+    assert np.array_equal(_host(acc, dt), of.add_factor_mul_slice_assign(c.copy(), a))
+    acc = _dev(c.copy()); gm.sub_factor_mul_slice_assign(s, acc, da)
+    assert np.array_equal(_host(acc, dt), of.sub_factor_mul_slice_assign(c.copy(), a))
+    # in-place alias (mul_assign)
+    ia = _dev(a.copy()); gm.reduce_mul_slice_assign(ia, db)
+    assert np.array_equal(_host(ia, dt), om.reduce_mul_slice_to(a, b))
+    # host-slice shims
+    ho = np.zeros(n, dtype=dt)
+    assert np.array_equal(gm.reduce_mul_slice_to(a, b, ho), om.reduce_mul_slice_to(a, b))
+    hacc = c.copy(); gm.reduce_add_mul_slice_assign(hacc, a, b)
+    assert np.array_equal(hacc, om.reduce_add_mul_slice_assign(c.copy(), a, b))
+
+
+def test_dcrt_per_limb_slice_ops():
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    moduli, n, rows = [Q50, Q50B, Q60], 1024, 3
+    rng = np.random.default_rng(3)
+    a = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in moduli]) for _ in range(rows)])
+    b = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in moduli]) for _ in range(rows)])
+    acc = np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in moduli]) for _ in range(rows)])
+    gm = P.BarrettModulus(moduli, 64, n=n)
+    want = acc.copy()
+    for li, m in enumerate(moduli):
+        for r in range(rows):
+            want[r, li] = O.BarrettModulus(m).reduce_add_mul_slice_assign(acc[r, li].copy(), a[r, li], b[r, li])
+    d = _dev(acc.copy())
+    gm.reduce_add_mul_slice_assign(d, _dev(a), _dev(b))
+    assert np.array_equal(_host(d, np.uint64), want)
+    # Shoup scalar MAC with one factor per limb (DcrtPolynomial::add_mul_factor_assign, dcrt/mul.rs:142-161)
+    factors = [int(rng.integers(0, m)) for m in moduli]
+    want = acc.copy()
+    for li, m in enumerate(moduli):
+        for r in range(rows):
+            want[r, li] = O.ShoupFactor(factors[li], m).add_factor_mul_slice_assign(acc[r, li].copy(), a[r, li])
+    d = _dev(acc.copy())
+    gm.add_factor_mul_slice_assign(factors, d, _dev(a))
+    assert np.array_equal(_host(d, np.uint64), want)
+
+
+@pytest.mark.parametrize("bits,q,log_basis,rev", [(32, Q27, 7, None), (32, Q27, 7, 2), (64, Q50, 7, None), (64, Q50, 7, 3),
+                                                  (32, 0b111000110, 3, 2), (64, 536813569, 4, 7), (64, Q60, 1, None),
+                                                  (64, Q60, 16, None), (32, Q27, 1, 5), (64, Q50, 25, None)])
+def test_decompose_matches_oracle(bits, q, log_basis, rev):
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    dt = np.uint64 if bits == 64 else np.uint32
+    ob = O.ApproxSignedBasis(q, log_basis, rev, bits)
+    gb = P.ApproxSignedBasis(q, log_basis, rev, bits)
+    assert gb.decompose_length() == ob.decompose_length() and gb.drop_bits() == ob.drop_bits()
+    rng = np.random.default_rng(11)
+    n = 10007
+    v = rng.integers(0, q, n, dtype=np.uint64).astype(dt)
+    v[:4] = [0, q - 1, q // 2, min(q - 1, (ob.threshold() or 1))]
+    want = ob.decompose_slice(v)
+    dig = torch.empty((gb.decompose_length(), n), dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
+    gb.decompose_batch(_dev(v), dig)
+    assert np.array_equal(_host(dig, dt), want)
+
+
+def test_rns_lift_and_extract_lwe():
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    moduli = [Q50, Q50B, Q60]
+    rng = np.random.default_rng(4)
+    for B in (2, 128, 5):
+        small = rng.integers(0, B, 1000, dtype=np.uint64)
+        want = O.RNSBase(moduli).wrapping_decompose_small_values_to(small, B)
+        out = torch.empty(3 * 1000, dtype=torch.int64, device="cuda")
+        P.RNSBase(moduli).wrapping_decompose_small_values_to(_dev(small), out, B)
+        assert np.array_equal(_host(out, np.uint64), want)
+    n, batch = 1024, 5
+    rl = rng.integers(0, Q27, (batch, 2 * n), dtype=np.uint64).astype(np.uint32)
+    rl[0, 1] = 0
+    out = torch.empty((batch, n + 1), dtype=torch.int32, device="cuda")
+    P.extract_lwe_batch(Q27, _dev(rl), out, n, 32)
+    got = _host(out, np.uint32)
+    for i in range(batch):
+        assert np.array_equal(got[i], O.extract_lwe(rl[i], Q27, 32))
