@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the polynomial-ring hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric "NTTs/s at N=4096" is quoted on):
+batched forward negacyclic NTT, N = 4096, 64-bit NTT-friendly prime q = 1125899906826241 (the reference's
+own bench prime, primus_ntt/benches/bench_u64.rs:8), batch 65536 polynomials (2 GiB) per GPU.
+A "step" is one pass of the hot path over the whole batch (one kernel launch, in place).
+
+  value  = whole-job NTTs/s with the batch resident in HBM (CUDA events, max over ranks)
+  e2e    = the same metric through the reference-facing C-ABI host-slice call
+           (pfhe_ntt64_transform_slices: pinned HOST buffer -> H2D -> kernel -> D2H, all inside the timed region)
+  roofline = algorithmic bytes (2*N*8 per NTT) / kernel time against the measured HBM copy peak
+  cpu_baseline = the CPU oracle (restated reference scalar path, OpenMP over the batch) on this box's cores
+  extra  = secondary numbers of the same path (INTT, fused polymul, external product, blind rotation = bootstraps/s)
+
+Multi-GPU: one process per GPU (torchrun), the batch is sharded (independent polynomials, no collective on
+the data path; NCCL only for the barrier / max-over-ranks of the timing) -> "scaling": "weak".
+
+`--impl reference` times the reference arm: the reference's CPU algorithm (oracle port, all host threads) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 12
+N = 1 << LOG_N
+Q = 1125899906826241
+BATCH = 65536
+BYTES_PER_NTT = 2 * N * 8            # read + write, SURVEY.md 8(d)
+MODMULS_PER_NTT = (N // 2) * LOG_N   # butterflies
+METRIC = "NTTs/s at N=4096 (u64 forward negacyclic NTT, batch 65536 per GPU)"
+UNIT = "NTT/s"
+CONFIG = {"workload": "batched forward NTT, N=4096, q=1125899906826241 (50-bit), batch 65536 polys (2 GiB) per GPU, in place",
+          "l2": "inputs (2 GiB) exceed L2 (126 MB): no flush needed between timed iterations",
+          "sharding": "independent polynomials split across GPUs, no data-path collective"}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # keep only samples under load (clock above idle) when there are any
+        loaded = [c for c in sm if c > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(sample_batch: int, reps: int):
+    """The reference's CPU path (oracle port): forward NTT over `sample_batch` polys, all host threads."""
+    import numpy as np
+    from oracle import oracle as O
+    t = O.U64NttTable(LOG_N, Q)
+    threads = O.max_threads()
+    rng = np.random.default_rng(0x5EED0002)
+    x = rng.integers(0, Q, (sample_batch, N), dtype=np.uint64)
+    t.forward_batch(x[:min(256, sample_batch)].copy(), threads)  # warm
+    best = 1e30
+    for _ in range(reps):
+        y = x.copy()
+        t0 = time.perf_counter()
+        t.forward_batch(y, threads)
+        best = min(best, time.perf_counter() - t0)
+    return sample_batch / best, threads, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = 16384
+    times = []
+    import numpy as np
+    from oracle import oracle as O
+    t = O.U64NttTable(LOG_N, Q)
+    threads = O.max_threads()
+    rng = np.random.default_rng(0x5EED0002)
+    x = rng.integers(0, Q, (sample, N), dtype=np.uint64)
+    for i in range(args.warmup + args.steps):
+        y = x.copy()
+        t0 = time.perf_counter()
+        t.forward_batch(y, threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": dict(CONFIG, reference_sample=f"{sample} polynomials per step (bounded sample of the 65536-poly batch)"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} NTTs/step x {args.steps} steps, OpenMP over the batch; the Rust reference cannot be "
+                                       "built here (no cargo) so this is the C restatement of its scalar Harvey path"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (extra) measurements")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import primus_fhe_b200 as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = args.batch
+    table = P.U64NttTable(LOG_N, Q, device=local_rank)
+    g = torch.Generator(device="cuda"); g.manual_seed(0x5EED0002 + rank)
+    data = torch.randint(0, Q, (batch, N), dtype=torch.int64, device="cuda", generator=g)
+
+    # ---- device-resident throughput (value) --------------------------------------------------------
+    for _ in range(args.warmup):
+        table.forward_batch(data)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = P.launch_count()
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record()
+    for a, b in evs:
+        a.record()
+        table.forward_batch(data)      # repeated forward transforms of transformed data: same work, still valid inputs (< q)
+        b.record()
+    e_all1.record()
+    barrier()
+    launches = P.launch_count() - launches0
+    total_ms = e_all0.elapsed_time(e_all1)
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_ms.item())
+    value = world * batch * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the C-ABI host-slice call (pinned host buffers) ----------------------------
+    e2e_batch = batch
+    host = torch.empty((e2e_batch, N), dtype=torch.int64).pin_memory()
+    host.copy_(data.cpu())
+    e2e_steps = max(2, min(args.steps, 5))
+    table.transform_slices(host)  # warm (streams, mempool)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        table.transform_slices(host)   # H2D + kernel + D2H of every polynomial, synchronous
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_batch * e2e_steps / float(t_e.item())
+    del host
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel ----------------------------------------------------------
+    peak, peak_src = _peaks()
+    avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = batch * BYTES_PER_NTT / (avg_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("ntt_fwd_u64_n4096", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": "ntt_kernel<u64,N=4096> forward", "algorithmic_bytes_per_launch": batch * BYTES_PER_NTT,
+                "avg_launch_ms": avg_kernel_ms,
+                "modmul": {"butterflies_per_s": batch * MODMULS_PER_NTT / (avg_kernel_ms * 1e-3),
+                           "note": "secondary bound: see DESIGN.md (integer / FP64 pipe butterfly rate measured by pfhe_modmul_microbench)"}}
+
+    # ---- CPU baseline (bounded sample) ---------------------------------------------------------------------
+    cpu_value, cores, cpu_s = cpu_reference(8192, 3)
+    cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"8192 NTTs (1/8 of the batch), best of 3, {cpu_s:.3f} s; C restatement of the reference's scalar "
+                              "Harvey NTT (the Rust reference cannot be built in this image)"}
+
+    # ---- secondary measurements (same hot path; a few launches each) ------------------------------------------
+    extra = {}
+    if not args.no_extra:
+        def timed(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return best * 1e-3
+        try:
+            extra["intt_per_s_n4096_u64"] = batch / timed(lambda: table.inverse_batch(data))
+            half = batch // 2
+            a_, b_, c_ = data[:half], data[half:], torch.empty_like(data[:half])
+            extra["polymul_per_s_n4096_u64"] = half / timed(lambda: table.polymul_batch(a_, b_, c_))
+            # C4-B external product: N=2048, k=1, base 2^7 (l=7), batch 4096, shared key
+            t11 = P.U64NttTable(11, Q, device=local_rank)
+            lv = P.ApproxSignedBasis(Q, 7, None, 64).decompose_length()
+            key = torch.randint(0, Q, (2 * lv * 2 * 2048,), dtype=torch.int64, device="cuda", generator=g)
+            cin = torch.randint(0, Q, (4096, 2 * 2048), dtype=torch.int64, device="cuda", generator=g)
+            cout = torch.empty_like(cin)
+            extra["external_products_per_s_n2048_u64_l7"] = 4096 / timed(lambda: t11.external_product_batch(1, 7, None, key, cin, cout, True))
+            # C5 blind rotation: n=512, N=1024, u32 q=132120577, base 2^7 (l=3); per-GPU share of the 10k batch
+            q32, nl = 132120577, 512
+            t10 = P.U32NttTable(10, q32, device=local_rank)
+            lv3 = P.ApproxSignedBasis(q32, 7, None, 32).decompose_length()
+            bsk = torch.randint(0, q32, (nl * 2 * lv3 * 2 * 1024,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+            nb = 1250
+            lwe = torch.randint(0, 2048, (nb, nl + 1), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+            tv = torch.randint(0, q32, (1024,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+            acc = torch.empty((nb, 2048), dtype=torch.int32, device="cuda")
+            extra["bootstraps_per_s_blind_rotation_n512_N1024_u32"] = nb / timed(lambda: t10.blind_rotate_batch(7, None, bsk, nl, lwe, tv, acc), reps=2)
+        except Exception as ex:  # secondary numbers must never hide the headline
+            extra["error"] = repr(ex)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": dict(CONFIG, batch_per_gpu=batch, n_gpus=world),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_batch * N * 8, "d2h_bytes_per_step": e2e_batch * N * 8,
+                    "api": "pfhe_ntt64_transform_slices (host-slice shim of NttTable::transform_slice, pinned host memory)",
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,51 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/pfhe.h declares, and reports the architecture it was compiled for.  No compute calls (no GPU here)."""
+import os
+import subprocess
+
+import primus_fhe_b200 as P
+
+
+def test_library_exports_every_declared_symbol():
+    lib = P._cabi.lib()
+    syms = P.declared_symbols()
+    assert len(syms) > 80
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.pfhe_compiled_arch() == b"sm_100a"
+    assert lib.pfhe_status_string(5) == b"ModulusTooLarge" and lib.pfhe_status_string(1) == b"NoPrimitiveRoot"
+
+
+def test_library_contains_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", P.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    archs = {line.split(".")[-2] for line in out.splitlines() if "sm_" in line and line.strip().endswith(".cubin")}
+    assert archs == {"sm_100a"}, out[:400]
+
+
+def test_no_product_code_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under primus_fhe_b200/ may reference it."""
+    root = os.path.dirname(P.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "pfhe_oracle" not in text, f
+
+
+def test_geometry_and_status_paths_without_gpu():
+    """Host-only entry points work without a device; device entry points fail loudly (no CPU fallback)."""
+    import ctypes as C
+    lv, dr = C.c_uint32(), C.c_uint32()
+    lib = P._cabi.lib()
+    lib.pfhe_basis64_geometry.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert lib.pfhe_basis64_geometry(1125899906826241, 7, 0, C.byref(lv), C.byref(dr)) == 0
+    assert (lv.value, dr.value) == (7, 1)        # l = 7, drop_bits = 1
+    lib.pfhe_basis32_geometry.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert lib.pfhe_basis32_geometry(132120577, 7, 0, C.byref(lv), C.byref(dr)) == 0
+    assert (lv.value, dr.value) == (3, 6)        # C4-A: l = 3, drop_bits = 6
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        lib.pfhe_ntt64_create.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
+        rc = lib.pfhe_ntt64_create(0, 12, 1125899906826241, C.byref(h))
+        assert rc == 8 and not h.value           # PFHE_ERR_CUDA: the product path refuses to run without a GPU

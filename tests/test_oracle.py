@@ -94,7 +94,7 @@ def test_barrett_and_shoup_exact(bits, q):
         assert m.reduce_mul_add(a, b, c) == (a * b + c) % q
         sf = O.ShoupFactor(a, q, bits)
         assert sf.quotient == (a << bits) // q
-        y = int(rng.integers(0, B))
+        y = int(rng.integers(0, B - 1, dtype=np.uint64, endpoint=True))
         lz = sf.lazy_factor_mul_modulo(y)
         assert lz < 2 * q and lz % q == a * y % q                      # shoup_factor.rs lazy < 2q
         assert sf.factor_mul_modulo(b) == m.reduce_mul(a, b)           # Shoup == Barrett
