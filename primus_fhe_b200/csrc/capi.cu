@@ -2,6 +2,7 @@
 // pipelined H2D -> kernel -> D2H path, and the thin device-batch forwarders.
 // No CPU compute path exists here: every transform / product is a kernel launch (no CPU fallback).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -135,6 +136,7 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     const auto &h = hd->h;
     const size_t n = h.n;
     std::vector<Pair> fwd(n), inv(n), fp, ip, fpl, ipl;
+    std::vector<double> fpf, ipf;
     for (size_t k = 0; k < n; k++) {
         fwd[k].x = h.roots[k];
         fwd[k].y = h.roots_q[k];
@@ -146,12 +148,24 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     const int loge = choose_loge(BITS, (int)log_n), loge_lat = lattice_loge(BITS, (int)log_n);
     if (loge) fill_pass_tables<T>(h, loge, fp, ip);
     if (loge_lat) fill_pass_tables<T>(h, loge_lat, fpl, ipl);
+    // FP64-pipe path: u64 words and q < 2^50 (every table value is then an exact double)
+    const char *no_f64 = getenv("PFHE_DISABLE_F64");
+    const bool use_f64 = BITS == 64 && loge != 0 && ((uint64_t)q >> 50) == 0 && !(no_f64 && no_f64[0] == '1');
+    if (use_f64) {
+        fpf.resize(fp.size());
+        ipf.resize(ip.size());
+        for (size_t i = 0; i < fp.size(); i++) {
+            fpf[i] = (double)fp[i].x;
+            ipf[i] = (double)ip[i].x;
+        }
+    }
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t sz_pair = sizeof(Pair);
     size_t off_fwd = 0, off_inv = align(off_fwd + n * sz_pair), off_fp = align(off_inv + n * sz_pair),
            off_ip = align(off_fp + fp.size() * sz_pair), off_fpl = align(off_ip + ip.size() * sz_pair),
            off_ipl = align(off_fpl + fpl.size() * sz_pair), off_ord = align(off_ipl + ipl.size() * sz_pair),
-           total = align(off_ord + 2 * n * sizeof(T));
+           off_fpf = align(off_ord + 2 * n * sizeof(T)), off_ipf = align(off_fpf + fpf.size() * sizeof(double)),
+           total = align(off_ipf + ipf.size() * sizeof(double));
     std::vector<unsigned char> stage(total, 0);
     memcpy(stage.data() + off_fwd, fwd.data(), n * sz_pair);
     memcpy(stage.data() + off_inv, inv.data(), n * sz_pair);
@@ -160,6 +174,8 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     if (!fpl.empty()) memcpy(stage.data() + off_fpl, fpl.data(), fpl.size() * sz_pair);
     if (!ipl.empty()) memcpy(stage.data() + off_ipl, ipl.data(), ipl.size() * sz_pair);
     memcpy(stage.data() + off_ord, h.ordinal.data(), 2 * n * sizeof(T));
+    if (!fpf.empty()) memcpy(stage.data() + off_fpf, fpf.data(), fpf.size() * sizeof(double));
+    if (!ipf.empty()) memcpy(stage.data() + off_ipf, ipf.data(), ipf.size() * sizeof(double));
     cudaError_t e = cudaMalloc(&hd->blob, total);
     if (e == cudaSuccess) e = cudaMemcpy(hd->blob, stage.data(), total, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -182,9 +198,16 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     d.fwd_pass = reinterpret_cast<const Pair *>(base + off_fp);
     d.inv_pass = reinterpret_cast<const Pair *>(base + off_ip);
     d.ordinal = reinterpret_cast<const T *>(base + off_ord);
+    d.fwd_pass_f = reinterpret_cast<const double *>(base + off_fpf);
+    d.inv_pass_f = reinterpret_cast<const double *>(base + off_ipf);
+    d.q_f = (double)q;
+    d.qinv_f = 1.0 / (double)q;
+    d.inv_n_f = (double)h.inv_n;
+    d.use_f64 = use_f64 ? 1u : 0u;
     hd->dev = d;
     hd->dev_lat = d;
     hd->dev_lat.loge = (uint32_t)loge_lat;
+    hd->dev_lat.use_f64 = 0;
     hd->dev_lat.fwd_pass = reinterpret_cast<const Pair *>(base + off_fpl);
     hd->dev_lat.inv_pass = reinterpret_cast<const Pair *>(base + off_ipl);
     *out = hd;
@@ -202,6 +225,7 @@ template <typename T> struct DcrtHandle {
     int device = 0;
     std::vector<NttHandle<T> *> limbs;
     DevNtt<T> *d_tables = nullptr;  // device array of the limb tables
+    DevNtt<T> tb0{};                // limb 0 by value (same field-policy flag as the device array)
 };
 
 // Pipelined host <-> device processing of `units` independent work items (`in_bytes`/`out_bytes` each).
@@ -372,7 +396,13 @@ static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size
     if (s == PFHE_OK) {
         DeviceGuard guard(device);
         std::vector<DevNtt<T>> tabs;
-        for (auto *h : d->limbs) tabs.push_back(h->dev);
+        bool all_f64 = true;
+        for (auto *h : d->limbs) all_f64 = all_f64 && h->dev.use_f64;
+        for (auto *h : d->limbs) {
+            tabs.push_back(h->dev);
+            tabs.back().use_f64 = all_f64 ? 1u : 0u;  // one field policy per launch
+        }
+        d->tb0 = tabs[0];
         cudaError_t e = cudaMalloc(&d->d_tables, tabs.size() * sizeof(DevNtt<T>));
         if (e == cudaSuccess) e = cudaMemcpy(d->d_tables, tabs.data(), tabs.size() * sizeof(DevNtt<T>), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) s = cuda_fail(e);
@@ -394,7 +424,7 @@ template <typename T, typename D> static pfhe_status dcrt_host_transform(const D
     const void *ins[1] = {polys};
     const size_t inb[1] = {bytes};
     return pipelined(t->device, ins, 1, inb, polys, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
-        return launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)L, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu * L, fwd, s);
+        return launch_ntt<T>(t->tb0, t->d_tables, (int)L, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu * L, fwd, s);
     });
 }
 
@@ -562,19 +592,19 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_forward_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        PFHE_CUDA(launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), true,         \
+        PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), true,         \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_inverse_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        PFHE_CUDA(launch_ntt<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), false,        \
+        PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), false,        \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_polymul_batch(const pfhe_dcrt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {       \
         if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
-        PFHE_CUDA(launch_polymul<T>(t->limbs[0]->dev, t->d_tables, (int)t->limbs.size(), a, b, c, batch * t->limbs.size(),            \
+        PFHE_CUDA(launch_polymul<T>(t->tb0, t->d_tables, (int)t->limbs.size(), a, b, c, batch * t->limbs.size(),            \
                                     static_cast<cudaStream_t>(stream)));                                                              \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \

@@ -81,7 +81,8 @@ template <typename V> __device__ __forceinline__ V ldg_vec(const V *p) {
 }
 
 template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
-    using Core = NttCore<T, LOGN, LOGE>;
+    using F = IntField<T>;
+    using Core = NttCore<F, LOGN, LOGE>;
     using Acc = typename AccOf<T>::type;
     static constexpr int N = Core::N, E = Core::E, TPP = Core::TPP, FB0 = Core::P::fb(0);
     static constexpr int CW = Core::CW, NV = Core::NV;
@@ -91,6 +92,7 @@ template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
     __device__ __forceinline__ static void accumulate(GetIn get, const T *__restrict__ key, const GadgetParams<T> &g, const DevNtt<T> &tb,
                                                       Acc (&acc)[COMPS][E], T *sm, int t, SyncF sync) {
         const T q = tb.q, two_q = tb.two_q;
+        const typename F::Ctx cx = F::ctx(tb);
         uint32_t terms = 0;
 #pragma unroll 1
         for (int r = 0; r < COMPS; r++) {
@@ -99,7 +101,7 @@ template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 T x[E];
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = gadget_digit<T>(g, get(r, Core::elem_index(FB0, t, j)), l);
-                Core::template fwd_from<0>(x, sm, tb, t, sync);
+                Core::template fwd_from<0>(x, sm, tb, cx, t, sync);
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = csub(csub(x[j], two_q), q);
                 const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
@@ -156,7 +158,7 @@ external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_const
 #pragma unroll
         for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
         if (to_coeff) {
-            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, EP::F::ctx(tb), t, sync);
             if (active) {
 #pragma unroll
                 for (int j = 0; j < E; j++) cout[(size_t)c * N + Core::elem_index(EP::FB0, t, j)] = x[j];
@@ -230,7 +232,7 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
             T x[E];
 #pragma unroll
             for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
-            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, EP::F::ctx(tb), t, sync);
             // ACC_c += result (each coefficient owned by exactly one thread)
 #pragma unroll
             for (int j = 0; j < E; j++) {

@@ -57,17 +57,19 @@ template <typename T> __device__ __forceinline__ DevNtt<T> pick_table(const DevN
 }
 
 // ------------------------------------------------------------------------------------------------
-// register-pass kernels
+// register-pass kernels (F = IntField<T> or F64Field)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int LOGN, int LOGE, int PPB, bool FWD>
+template <typename F, int LOGN, int LOGE, int PPB, bool FWD>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
-ntt_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *__restrict__ src,
-           T *__restrict__ dst, size_t npolys) {
-    using Core = NttCore<T, LOGN, LOGE>;
+ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
+           const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
+    using Core = NttCore<F, LOGN, LOGE>;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
     constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
-    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw) + (size_t)grp * N;
     size_t poly = (size_t)blockIdx.x * PPB + grp;
     const bool active = poly < npolys;
     if (!active) {
@@ -75,35 +77,35 @@ ntt_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ 
         poly = npolys - 1;
     }
     const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    const typename F::Ctx c = F::ctx(tb);
     const T *g_in = src + poly * N;
     T *g_out = dst + poly * N;
     typename SyncFor<TPP>::type sync;
-    T x[E];
+    Elem x[E];
     if (FWD) {
-        Core::forward_g2r(g_in, x, sm, tb, t, sync);
-        if (active) Core::sm_store<Core::P::NPASS - 1>(x, sm, t);
+        Core::forward_g2r(g_in, x, sm, tb, c, t, sync);
+        if (active) Core::fwd_regs_to_sm(x, sm, c, t);
         sync();
         if (active) Core::copy_s2g(sm, g_out, t);
     } else {
-        Core::load_g2r(g_in, x, sm, t, sync);
-        Core::inv_from<Core::P::NPASS - 1>(x, sm, tb, t, sync);
-        if (active) {
-            constexpr int FB0 = Core::P::fb(0);
-#pragma unroll
-            for (int j = 0; j < E; j++) g_out[Core::elem_index(FB0, t, j)] = x[j];
-        }
+        Core::load_g2r(g_in, x, sm, c, t, sync);
+        Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, c, t, sync);
+        if (active) Core::inv_regs_to_global(x, g_out, c, t);
     }
 }
 
-template <typename T, int LOGN, int LOGE, int PPB>
+template <typename F, int LOGN, int LOGE, int PPB>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
-polymul_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *__restrict__ a,
-               const T *__restrict__ b, T *__restrict__ c, size_t npolys) {
-    using Core = NttCore<T, LOGN, LOGE>;
+polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
+               const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, typename F::WordT *__restrict__ cc,
+               size_t npolys) {
+    using Core = NttCore<F, LOGN, LOGE>;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
     constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
-    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw) + (size_t)grp * N;
     size_t poly = (size_t)blockIdx.x * PPB + grp;
     const bool active = poly < npolys;
     if (!active) {
@@ -111,20 +113,16 @@ polymul_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restric
         poly = npolys - 1;
     }
     const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    const typename F::Ctx c = F::ctx(tb);
     typename SyncFor<TPP>::type sync;
-    T xa[E], xb[E];
-    Core::forward_g2r(a + poly * N, xa, sm, tb, t, sync);
-    Core::forward_g2r(b + poly * N, xb, sm, tb, t, sync);
+    Elem xa[E], xb[E];
+    Core::forward_g2r(a + poly * N, xa, sm, tb, c, t, sync);
+    Core::forward_g2r(b + poly * N, xb, sm, tb, c, t, sync);
     // pointwise product, exact mod q (BarrettModulus::reduce_mul, primus_modulus/src/barrett/ops.rs:276-283)
 #pragma unroll
-    for (int j = 0; j < E; j++) xa[j] = barrett_mul<T>(tb.br, xa[j], xb[j]);
-    Core::inv_from<Core::P::NPASS - 1>(xa, sm, tb, t, sync);
-    if (active) {
-        constexpr int FB0 = Core::P::fb(0);
-        T *g_out = c + poly * N;
-#pragma unroll
-        for (int j = 0; j < E; j++) g_out[Core::elem_index(FB0, t, j)] = xa[j];
-    }
+    for (int j = 0; j < E; j++) xa[j] = F::pointwise(xa[j], xb[j], c);
+    Core::template inv_from<Core::P::NPASS - 1>(xa, sm, tb, c, t, sync);
+    if (active) Core::inv_regs_to_global(xa, cc + poly * N, c, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,37 +255,59 @@ __global__ void monomial_kernel(const __grid_constant__ DevNtt<T> tb, T coeff, T
 // ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
-template <typename T, int LOGN, int LOGE, int PPB>
-static cudaError_t run_ntt(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys, bool fwd,
-                           cudaStream_t stream) {
+template <typename F, int LOGN, int LOGE, int PPB>
+static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<typename F::WordT> *tables, int limbs,
+                             const typename F::WordT *src, typename F::WordT *dst, size_t npolys, bool fwd, cudaStream_t stream) {
+    using T = typename F::WordT;
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
     cudaError_t e;
     if (fwd) {
-        auto k = ntt_kernel<T, LOGN, LOGE, PPB, true>;
+        auto k = ntt_kernel<F, LOGN, LOGE, PPB, true>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
     } else {
-        auto k = ntt_kernel<T, LOGN, LOGE, PPB, false>;
+        auto k = ntt_kernel<F, LOGN, LOGE, PPB, false>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
     }
     count_launch();
     return cudaGetLastError();
 }
-template <typename T, int LOGN, int LOGE, int PPB>
-static cudaError_t run_polymul(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c, size_t npolys,
-                               cudaStream_t stream) {
+template <typename F, int LOGN, int LOGE, int PPB>
+static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<typename F::WordT> *tables, int limbs,
+                                 const typename F::WordT *a, const typename F::WordT *b, typename F::WordT *c, size_t npolys,
+                                 cudaStream_t stream) {
+    using T = typename F::WordT;
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
-    auto k = polymul_kernel<T, LOGN, LOGE, PPB>;
+    auto k = polymul_kernel<F, LOGN, LOGE, PPB>;
     cudaError_t e;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
     count_launch();
     return cudaGetLastError();
+}
+
+
+// field selection: u64 tables with q < 2^50 run on the FP64 pipe, everything else on the integer pipe
+template <typename T, int LOGN, int LOGE, int PPB>
+static cudaError_t run_ntt(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys, bool fwd,
+                           cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (tb0.use_f64) return run_ntt_f<F64Field, LOGN, LOGE, PPB>(tb0, tables, limbs, src, dst, npolys, fwd, stream);
+    }
+    return run_ntt_f<IntField<T>, LOGN, LOGE, PPB>(tb0, tables, limbs, src, dst, npolys, fwd, stream);
+}
+template <typename T, int LOGN, int LOGE, int PPB>
+static cudaError_t run_polymul(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c, size_t npolys,
+                               cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (tb0.use_f64) return run_polymul_f<F64Field, LOGN, LOGE, PPB>(tb0, tables, limbs, a, b, c, npolys, stream);
+    }
+    return run_polymul_f<IntField<T>, LOGN, LOGE, PPB>(tb0, tables, limbs, a, b, c, npolys, stream);
 }
 
 template <typename T> static int generic_threads(int log_n) {

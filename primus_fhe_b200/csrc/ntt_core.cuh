@@ -33,6 +33,11 @@ template <typename T> struct DevNtt {
     const Pair *fwd_pass;  // per-pass [slot][high] layouts (see Plan)
     const Pair *inv_pass;
     const T *ordinal;      // psi^k, k < 2N (monomial transforms, table.rs:330-338)
+    // FP64-pipe path (u64 words, q < 2^50): twiddles as exact doubles, same [slot][high] pass layout
+    const double *fwd_pass_f;
+    const double *inv_pass_f;
+    double q_f, qinv_f, inv_n_f;
+    uint32_t use_f64;
 };
 
 template <typename T> __device__ __forceinline__ typename Word<T>::Pair ld_pair(const typename Word<T>::Pair *p) { return __ldg(p); }
@@ -81,9 +86,132 @@ struct PlanRt {
     __host__ int total() const { return pass_offset(npass); }
 };
 
-template <typename T, int LOGN, int LOGE> struct NttCore {
+
+// ======================================================================================================
+// Field policies: how one butterfly is computed.  Both give bit-identical canonical results.
+// ======================================================================================================
+
+// Integer pipe: Harvey lazy butterflies with Shoup twiddles (the reference's scalar algorithm,
+// primus_ntt/src/ntt/prime64/scalar/arithmetic.rs:32-79).  Any q < 2^(BITS-2).
+template <typename T> struct IntField {
+    using WordT = T;
+    using Elem = T;
+    using Tw = typename Word<T>::Pair;
+    struct Ctx {
+        T q, two_q, inv_n, inv_n_q;
+        Barrett<T> br;
+    };
+    __device__ __forceinline__ static Ctx ctx(const DevNtt<T> &tb) { return Ctx{tb.q, tb.two_q, tb.inv_n, tb.inv_n_q, tb.br}; }
+    __device__ __forceinline__ static const Tw *fwd_tw(const DevNtt<T> &tb) { return tb.fwd_pass; }
+    __device__ __forceinline__ static const Tw *inv_tw(const DevNtt<T> &tb) { return tb.inv_pass; }
+    __device__ __forceinline__ static Tw ld(const Tw *p) { return __ldg(p); }
+    __device__ __forceinline__ static Elem load(T w, const Ctx &) { return w; }          // fwd: < 4q, inv: < 2q
+    __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &) { return raw; }
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c) { fwd_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
+    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c) { inv_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
+    // final inverse stage fused with n^-1 (transform.rs:283-318); outputs canonical
+    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+        const T tx = x + y, ty = x + c.two_q - y;
+        x = shoup<T>(tx, c.inv_n, c.inv_n_q, c.q);
+        y = shoup<T>(ty, w.x, w.y, c.q);
+    }
+    __device__ __forceinline__ static T fwd_word(Elem v, const Ctx &c) { return csub(csub(v, c.two_q), c.q); }
+    __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return fwd_word(v, c); }
+    __device__ __forceinline__ static T inv_word(Elem v, const Ctx &) { return v; }
+    // forward outputs a, b -> a*b mod q as an inverse-transform input (BarrettModulus::reduce_mul)
+    __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return barrett_mul<T>(c.br, fwd_word(a, c), fwd_word(b, c)); }
+};
+
+// FP64 pipe (B200 keeps full-rate FP64: 64 DFMA/clk/SM, while a 64x64-bit integer product costs ~4 half-rate
+// IMAD.WIDE).  Values are integers held exactly in doubles, |v| < 2q < 2^51; q < 2^50.
+//   mulmod(y, w): P = y*w as (h, l) = (RN(P), P - h)  [exact, fma];  c = rint(h * RN(1/q))  [magic-constant rounding];
+//   r = (h - c*q) + l  is exact and |r| < q  because |c - P/q| < 1/2 + |P/q| 2^-52 < 1  for |y| < 2q <= 2^51 - 2.
+// Results are the same residues the integer path produces; the canonical output is bit-identical.
+struct F64Field {
+    using WordT = uint64_t;
+    using Elem = double;
+    using Tw = double;
+    struct Ctx {
+        double q, qinv, inv_n;
+        uint32_t q_hi, q_lo;
+    };
+    static constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    static constexpr double kTwo52 = 4503599627370496.0;
+    __device__ __forceinline__ static Ctx ctx(const DevNtt<uint64_t> &tb) {
+        return Ctx{tb.q_f, tb.qinv_f, tb.inv_n_f, (uint32_t)__double2hiint(tb.q_f), (uint32_t)__double2loint(tb.q_f)};
+    }
+    __device__ __forceinline__ static const Tw *fwd_tw(const DevNtt<uint64_t> &tb) { return tb.fwd_pass_f; }
+    __device__ __forceinline__ static const Tw *inv_tw(const DevNtt<uint64_t> &tb) { return tb.inv_pass_f; }
+    __device__ __forceinline__ static Tw ld(const Tw *p) { return __ldg(p); }
+
+    __device__ __forceinline__ static double mulmod(double y, double w, const Ctx &c) {
+        const double h = __dmul_rn(y, w);
+        const double l = __fma_rn(y, w, -h);
+        const double t = __fma_rn(h, c.qinv, kMagic);
+        const double k = __dsub_rn(t, kMagic);
+        const double d = __fma_rn(-k, c.q, h);
+        return __dadd_rn(d, l);
+    }
+    // (-2q, 2q) -> (-q, q): subtract copysign(q, x) when |x| >= q; the compare/select run on the integer ALU
+    __device__ __forceinline__ static double fold(double x, const Ctx &c) {
+        const uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
+        const uint32_t ahi = hi & 0x7fffffffu;
+        const bool ge = (ahi > c.q_hi) || (ahi == c.q_hi && lo >= c.q_lo);
+        const uint32_t shi = ge ? (c.q_hi | (hi & 0x80000000u)) : 0u;
+        const uint32_t slo = ge ? c.q_lo : 0u;
+        return __dsub_rn(x, __hiloint2double((int)shi, (int)slo));
+    }
+    // exact u64 (< 2^52) -> double without the slow conversion pipe
+    __device__ __forceinline__ static double from_u64(uint64_t v) {
+        return __dsub_rn(__hiloint2double((int)(0x43300000u | (uint32_t)(v >> 32)), (int)(uint32_t)v), kTwo52);
+    }
+    __device__ __forceinline__ static uint64_t to_u64(double v) {  // v integer in [0, 2^52)
+        const double t = __dadd_rn(v, kTwo52);
+        return ((uint64_t)((uint32_t)__double2hiint(t) & 0x000fffffu) << 32) | (uint32_t)__double2loint(t);
+    }
+    // inputs may be lazy (< 4q forward, < 2q inverse): bring to [0, 2q) / fold
+    __device__ __forceinline__ static Elem load(uint64_t w, const Ctx &c) {
+        double v = from_u64(w);
+        const double two_q = __dadd_rn(c.q, c.q);
+        if (v >= two_q) v = __dsub_rn(v, two_q);
+        return fold(v, c);
+    }
+    __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &c) { return load((uint64_t)__double_as_longlong(raw), c); }
+    // |x|,|y| < 2q on entry and exit
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+        const double xt = fold(x, c);
+        const double t = mulmod(y, w, c);
+        x = __dadd_rn(xt, t);
+        y = __dsub_rn(xt, t);
+    }
+    // |x|,|y| < q on entry and exit
+    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+        const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
+        x = fold(s, c);
+        y = mulmod(d, w, c);
+    }
+    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+        const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
+        x = mulmod(s, c.inv_n, c);
+        y = mulmod(d, w, c);
+    }
+    __device__ __forceinline__ static uint64_t canon(double v, const Ctx &c) {  // (-q, q) -> [0, q)
+        if (v < 0.0) v = __dadd_rn(v, c.q);
+        return to_u64(v);
+    }
+    __device__ __forceinline__ static uint64_t fwd_word(Elem v, const Ctx &c) { return canon(fold(v, c), c); }
+    __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)fwd_word(v, c)); }
+    __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) { return canon(v, c); }
+    __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return mulmod(fold(a, c), fold(b, c), c); }
+};
+
+template <typename F, int LOGN, int LOGE> struct NttCore {
     using P = Plan<LOGN, LOGE>;
-    using Pair = typename Word<T>::Pair;
+    using T = typename F::WordT;   // word type in global memory
+    using Elem = typename F::Elem; // register / shared-memory representation
+    using Tw = typename F::Tw;
+    using Ctx = typename F::Ctx;
+    static_assert(sizeof(Elem) == sizeof(T), "exchange buffer elements are word sized");
     static constexpr int N = P::N, E = P::E, TPP = P::TPP;
     static constexpr int CW = 16 / sizeof(T);                // words per 16-byte chunk
     static constexpr int SW_DST = (sizeof(T) == 8) ? 1 : 2;  // log2(CW)
@@ -93,6 +221,9 @@ template <typename T, int LOGN, int LOGE> struct NttCore {
     static_assert(E >= CW, "a thread row must hold at least one 16-byte chunk");
 
     struct alignas(16) Vec {
+        Elem v[CW];
+    };
+    struct alignas(16) WVec {
         T v[CW];
     };
 
@@ -104,57 +235,50 @@ template <typename T, int LOGN, int LOGE> struct NttCore {
     }
 
     // ---- register passes -------------------------------------------------------------------
-    template <int PASS> __device__ __forceinline__ static void fwd_pass_regs(T (&x)[E], const DevNtt<T> &tb, int t) {
+    template <int PASS> __device__ __forceinline__ static void fwd_pass_regs(Elem (&x)[E], const DevNtt<T> &tb, const Ctx &c, int t) {
         constexpr int NS = P::nstages(PASS), FB = P::fb(PASS), NH = P::nh(PASS);
-        const Pair *tw = tb.fwd_pass + P::pass_offset(PASS);
+        const Tw *tw = F::fwd_tw(tb) + P::pass_offset(PASS);
         const int high = (t >> FB);
-        const T q = tb.q, two_q = tb.two_q;
 #pragma unroll
         for (int ls = 0; ls < NS; ls++) {
             const int jb = LOGE - 1 - ls;
 #pragma unroll
             for (int jp = 0; jp < (1 << ls); jp++) {
-                const Pair w = ld_pair<T>(tw + (((1 << ls) - 1 + jp) * NH + high));
+                const Tw w = F::ld(tw + (((1 << ls) - 1 + jp) * NH + high));
 #pragma unroll
                 for (int jl = 0; jl < (1 << jb); jl++) {
                     const int j0 = (jp << (jb + 1)) | jl, j1 = j0 | (1 << jb);
-                    fwd_bfly<T>(x[j0], x[j1], w.x, w.y, q, two_q);
+                    F::fwd(x[j0], x[j1], w, c);
                 }
             }
         }
     }
 
-    // inverse pass; LASTSCALE: this pass contains the final stage fused with n^-1
-    template <int PASS> __device__ __forceinline__ static void inv_pass_regs(T (&x)[E], const DevNtt<T> &tb, int t) {
+    // inverse pass; pass 0 contains the final stage fused with n^-1
+    template <int PASS> __device__ __forceinline__ static void inv_pass_regs(Elem (&x)[E], const DevNtt<T> &tb, const Ctx &c, int t) {
         constexpr int NS = P::nstages(PASS), FB = P::fb(PASS), NH = P::nh(PASS);
-        const Pair *tw = tb.inv_pass + P::pass_offset(PASS);
+        const Tw *tw = F::inv_tw(tb) + P::pass_offset(PASS);
         const int high = (t >> FB);
-        const T q = tb.q, two_q = tb.two_q;
 #pragma unroll
         for (int ls = NS - 1; ls >= 0; ls--) {
             const int jb = LOGE - 1 - ls;
 #pragma unroll
             for (int jp = 0; jp < (1 << ls); jp++) {
-                const Pair w = ld_pair<T>(tw + (((1 << ls) - 1 + jp) * NH + high));
+                const Tw w = F::ld(tw + (((1 << ls) - 1 + jp) * NH + high));
 #pragma unroll
                 for (int jl = 0; jl < (1 << jb); jl++) {
                     const int j0 = (jp << (jb + 1)) | jl, j1 = j0 | (1 << jb);
-                    if (PASS == 0 && ls == 0) {
-                        // final stage: x' = inv_n*(x+y), y' = inv_n_w*(x+2q-y)  (transform.rs:283-318)
-                        T tx = x[j0] + x[j1];
-                        T ty = x[j0] + two_q - x[j1];
-                        x[j0] = shoup<T>(tx, tb.inv_n, tb.inv_n_q, q);
-                        x[j1] = shoup<T>(ty, w.x, w.y, q);
-                    } else {
-                        inv_bfly<T>(x[j0], x[j1], w.x, w.y, q, two_q);
-                    }
+                    if (PASS == 0 && ls == 0)
+                        F::inv_last(x[j0], x[j1], w, c);
+                    else
+                        F::inv(x[j0], x[j1], w, c);
                 }
             }
         }
     }
 
     // ---- shared-memory exchange (canonical index order, swizzled) ---------------------------
-    template <int PASS> __device__ __forceinline__ static void sm_store(const T (&x)[E], T *sm, int t) {
+    template <int PASS> __device__ __forceinline__ static void sm_store(const Elem (&x)[E], Elem *sm, int t) {
         constexpr int FB = P::fb(PASS);
         if constexpr (FB == 0) {
 #pragma unroll
@@ -169,7 +293,7 @@ template <typename T, int LOGN, int LOGE> struct NttCore {
             for (int j = 0; j < E; j++) sm[swz(elem_index(FB, t, j))] = x[j];
         }
     }
-    template <int PASS> __device__ __forceinline__ static void sm_load(T (&x)[E], const T *sm, int t) {
+    template <int PASS> __device__ __forceinline__ static void sm_load(Elem (&x)[E], const Elem *sm, int t) {
         constexpr int FB = P::fb(PASS);
         if constexpr (FB == 0) {
 #pragma unroll
@@ -184,78 +308,80 @@ template <typename T, int LOGN, int LOGE> struct NttCore {
         }
     }
 
-    // coalesced 128-bit copy between global memory (natural order) and the swizzled buffer
-    __device__ __forceinline__ static void copy_g2s(const T *g, T *sm, int t) {
+    // coalesced 128-bit copy between global memory (natural order, raw words) and the swizzled buffer
+    __device__ __forceinline__ static void copy_g2s(const T *g, Elem *sm, int t) {
 #pragma unroll
         for (int v = t; v < N / CW; v += TPP) {
-            Vec d = *reinterpret_cast<const Vec *>(g + v * CW);
-            *reinterpret_cast<Vec *>(sm + swz(v * CW)) = d;
+            const WVec d = *reinterpret_cast<const WVec *>(g + v * CW);
+            *reinterpret_cast<WVec *>(sm + swz(v * CW)) = d;
         }
     }
-    __device__ __forceinline__ static void copy_s2g(const T *sm, T *g, int t) {
+    __device__ __forceinline__ static void copy_s2g(const Elem *sm, T *g, int t) {
 #pragma unroll
         for (int v = t; v < N / CW; v += TPP) {
-            Vec d = *reinterpret_cast<const Vec *>(sm + swz(v * CW));
-            *reinterpret_cast<Vec *>(g + v * CW) = d;
+            const WVec d = *reinterpret_cast<const WVec *>(sm + swz(v * CW));
+            *reinterpret_cast<WVec *>(g + v * CW) = d;
         }
     }
 
     // ---- recursive pass drivers ---------------------------------------------------------------
     // forward passes PASS..NPASS-1 with x holding pass PASS's elements on entry; on exit x holds the
-    // last pass's elements (thread t owns words [t*E, (t+1)*E)), values in [0,4q).
-    template <int PASS, typename SyncF> __device__ __forceinline__ static void fwd_from(T (&x)[E], T *sm, const DevNtt<T> &tb, int t, SyncF sync) {
-        fwd_pass_regs<PASS>(x, tb, t);
+    // last pass's elements (thread t owns words [t*E, (t+1)*E)), lazy representation.
+    template <int PASS, typename SyncF>
+    __device__ __forceinline__ static void fwd_from(Elem (&x)[E], Elem *sm, const DevNtt<T> &tb, const Ctx &c, int t, SyncF sync) {
+        fwd_pass_regs<PASS>(x, tb, c, t);
         if constexpr (PASS + 1 < P::NPASS) {
             sm_store<PASS>(x, sm, t);
             sync();
             sm_load<PASS + 1>(x, sm, t);
             sync();  // buffer may be rewritten by the next exchange
-            fwd_from<PASS + 1>(x, sm, tb, t, sync);
+            fwd_from<PASS + 1>(x, sm, tb, c, t, sync);
         }
     }
-    // inverse passes PASS..0 with x holding pass PASS's elements (values < 2q) on entry; on exit x holds
-    // pass 0's elements, canonical.
-    template <int PASS, typename SyncF> __device__ __forceinline__ static void inv_from(T (&x)[E], T *sm, const DevNtt<T> &tb, int t, SyncF sync) {
-        inv_pass_regs<PASS>(x, tb, t);
+    // inverse passes PASS..0 with x holding pass PASS's elements on entry; on exit x holds pass 0's
+    // elements in final form (F::inv_word gives the canonical word).
+    template <int PASS, typename SyncF>
+    __device__ __forceinline__ static void inv_from(Elem (&x)[E], Elem *sm, const DevNtt<T> &tb, const Ctx &c, int t, SyncF sync) {
+        inv_pass_regs<PASS>(x, tb, c, t);
         if constexpr (PASS > 0) {
             sm_store<PASS>(x, sm, t);
             sync();
             sm_load<PASS - 1>(x, sm, t);
             sync();
-            inv_from<PASS - 1>(x, sm, tb, t, sync);
+            inv_from<PASS - 1>(x, sm, tb, c, t, sync);
         }
     }
 
     // ---- whole transforms -----------------------------------------------------------------------
-    // forward: global (natural order, strided coalesced loads) -> registers of the last pass, canonical
-    template <typename SyncF> __device__ __forceinline__ static void forward_g2r(const T *g, T (&x)[E], T *sm, const DevNtt<T> &tb, int t, SyncF sync) {
+    // forward: global (natural order, strided coalesced loads) -> registers of the last pass (lazy form)
+    template <typename SyncF>
+    __device__ __forceinline__ static void forward_g2r(const T *g, Elem (&x)[E], Elem *sm, const DevNtt<T> &tb, const Ctx &c, int t, SyncF sync) {
         constexpr int FB0 = P::fb(0);
 #pragma unroll
-        for (int j = 0; j < E; j++) x[j] = g[elem_index(FB0, t, j)];
-        fwd_from<0>(x, sm, tb, t, sync);
-        const T q = tb.q, two_q = tb.two_q;
+        for (int j = 0; j < E; j++) x[j] = F::load(g[elem_index(FB0, t, j)], c);
+        fwd_from<0>(x, sm, tb, c, t, sync);
+    }
+    // forward outputs in registers -> canonical words in the swizzled buffer (then copy_s2g)
+    __device__ __forceinline__ static void fwd_regs_to_sm(const Elem (&x)[E], Elem *sm, const Ctx &c, int t) {
+        Elem y[E];
 #pragma unroll
-        for (int j = 0; j < E; j++) x[j] = csub(csub(x[j], two_q), q);
+        for (int j = 0; j < E; j++) y[j] = F::fwd_bits(x[j], c);
+        sm_store<P::NPASS - 1>(y, sm, t);
     }
-    // registers of the last pass -> global (bit-reversed order == in-place order), coalesced via the buffer
-    template <typename SyncF> __device__ __forceinline__ static void store_r2g(const T (&x)[E], T *g, T *sm, int t, SyncF sync) {
-        sm_store<P::NPASS - 1>(x, sm, t);
-        sync();
-        copy_s2g(sm, g, t);
-    }
-    // global (bit-reversed order) -> registers of the last pass
-    template <typename SyncF> __device__ __forceinline__ static void load_g2r(const T *g, T (&x)[E], T *sm, int t, SyncF sync) {
+    // global (bit-reversed order) -> registers of the last pass, as inverse-transform inputs
+    template <typename SyncF> __device__ __forceinline__ static void load_g2r(const T *g, Elem (&x)[E], Elem *sm, const Ctx &c, int t, SyncF sync) {
         copy_g2s(g, sm, t);
         sync();
         sm_load<P::NPASS - 1>(x, sm, t);
         sync();
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = F::load_bits(x[j], c);
     }
-    // inverse: registers of the last pass -> global (natural order), canonical
-    template <typename SyncF> __device__ __forceinline__ static void inverse_r2g(T (&x)[E], T *g, T *sm, const DevNtt<T> &tb, int t, SyncF sync) {
-        inv_from<P::NPASS - 1>(x, sm, tb, t, sync);
+    // inverse outputs (pass-0 layout) -> global, natural order, canonical
+    __device__ __forceinline__ static void inv_regs_to_global(const Elem (&x)[E], T *g, const Ctx &c, int t) {
         constexpr int FB0 = P::fb(0);
 #pragma unroll
-        for (int j = 0; j < E; j++) g[elem_index(FB0, t, j)] = x[j];
+        for (int j = 0; j < E; j++) g[elem_index(FB0, t, j)] = F::inv_word(x[j], c);
     }
 };
 
