@@ -98,8 +98,12 @@ class _NttTable:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
-            f(h); self._h = None
+            try:
+                f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
 
     def _scalar(self, name):
         f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p]; f.restype = _ct(self.bits)
@@ -239,8 +243,12 @@ class _DcrtTable:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
-            f(h); self._h = None
+            try:
+                f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
 
     def _size(self, name):
         f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p]; f.restype = C.c_size_t

@@ -152,11 +152,12 @@ struct F64Field {
         const double d = __fma_rn(-k, c.q, h);
         return __dadd_rn(d, l);
     }
-    // (-2q, 2q) -> (-q, q): subtract copysign(q, x) when |x| >= q; the compare/select run on the integer ALU
+    // (-2q, 2q) -> (-q, q): subtract copysign(q, x) when |x| >= th, where th <= q is q with the low mantissa word
+    // cleared (th > q - 2^29).  Folding a little early is harmless (|x - q| < q still holds for x in [th, 2q)), and it
+    // lets the test look at the high word only: 1 ISETP + 2 LOP3 + 2 SEL on the integer ALU, 1 DADD on the FP64 pipe.
     __device__ __forceinline__ static double fold(double x, const Ctx &c) {
-        const uint32_t hi = (uint32_t)__double2hiint(x), lo = (uint32_t)__double2loint(x);
-        const uint32_t ahi = hi & 0x7fffffffu;
-        const bool ge = (ahi > c.q_hi) || (ahi == c.q_hi && lo >= c.q_lo);
+        const uint32_t hi = (uint32_t)__double2hiint(x);
+        const bool ge = (hi & 0x7fffffffu) >= c.q_hi;
         const uint32_t shi = ge ? (c.q_hi | (hi & 0x80000000u)) : 0u;
         const uint32_t slo = ge ? c.q_lo : 0u;
         return __dsub_rn(x, __hiloint2double((int)shi, (int)slo));
