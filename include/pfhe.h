@@ -119,7 +119,8 @@ pfhe_status pfhe_ntt32_transform_coeff_one_monomial(const pfhe_ntt32 *t, size_t 
 pfhe_status pfhe_ntt64_transform_coeff_minus_one_monomial(const pfhe_ntt64 *t, size_t degree, uint64_t *values);
 pfhe_status pfhe_ntt32_transform_coeff_minus_one_monomial(const pfhe_ntt32 *t, size_t degree, uint32_t *values);
 
-/* Device batch API (stream ordered, in place, `dev` = [batch][N] DEVICE words). */
+/* Device batch API (stream ordered, in place, `dev` = [batch][N] DEVICE words, canonical values in [0,q);
+ * lazy-range data must first go through PFHE_OP_REDUCE_LAZY -- the host-slice shims do that themselves). */
 pfhe_status pfhe_ntt64_forward_batch(const pfhe_ntt64 *t, uint64_t *dev, size_t batch, void *stream);
 pfhe_status pfhe_ntt32_forward_batch(const pfhe_ntt32 *t, uint32_t *dev, size_t batch, void *stream);
 pfhe_status pfhe_ntt64_inverse_batch(const pfhe_ntt64 *t, uint64_t *dev, size_t batch, void *stream);
@@ -195,7 +196,8 @@ typedef enum {
     PFHE_OP_ADD_MUL_SCALAR = 8, /* out = out + a*s reduce_add_mul_scalar_slice_assign            */
     PFHE_OP_FACTOR_MUL = 9,  /* out = f*a  (Shoup) FactorSliceOps::factor_mul_slice_to (primus_factor/src/ops.rs:58-118) */
     PFHE_OP_ADD_FACTOR_MUL = 10, /* out += f*a     add_factor_mul_slice_assign (common/slice.rs:61-70)   */
-    PFHE_OP_SUB_FACTOR_MUL = 11  /* out -= f*a     sub_factor_mul_slice_assign                   */
+    PFHE_OP_SUB_FACTOR_MUL = 11, /* out -= f*a     sub_factor_mul_slice_assign                   */
+    PFHE_OP_REDUCE_LAZY = 12     /* out = a mod q for a in [0,4q): canonicalises lazy-range inputs (reduce_once twice) */
 } pfhe_slice_op;
 
 /* One entry point per word size; `scalars` (HOST, `limbs` words) holds s / f per limb for the

@@ -289,14 +289,22 @@ static pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
     return status;
 }
 
-template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd) {
+template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd, bool lazy = false) {
     if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
     const size_t bytes = sizeof(T) << t->h.log_n;
     const void *ins[1] = {polys};
     const size_t inb[1] = {bytes};
     // in place on the device: the "out" region doubles as the input region (n_in = 0 inputs + copy in manually)
     return pipelined(t->device, ins, 1, inb, polys, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
-        return launch_ntt<T>(t->dev, nullptr, 1, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu, fwd, s);
+        const T *src = static_cast<const T *>(din[0]);
+        if (lazy) {  // lazy trait contract: inputs in [0,4q) / [0,2q) -> canonicalise on the device first
+            LimbConsts<T> lc{};
+            lc.br[0] = t->dev.br;
+            cudaError_t e = launch_slice_op<T>(PFHE_OP_REDUCE_LAZY, lc, 1, src, nullptr, nullptr, const_cast<T *>(src), nu,
+                                               (size_t)1 << t->h.log_n, s);
+            if (e != cudaSuccess) return e;
+        }
+        return launch_ntt<T>(t->dev, nullptr, 1, src, static_cast<T *>(dout), nu, fwd, s);
     });
 }
 
@@ -355,7 +363,7 @@ template <typename T> static pfhe_status make_limb_consts(const T *moduli, size_
 template <typename T>
 static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
                                 size_t n, void *stream) {
-    if (op < 0 || op > PFHE_OP_SUB_FACTOR_MUL) return PFHE_ERR_INVALID_ARG;
+    if (op < 0 || op > PFHE_OP_REDUCE_LAZY) return PFHE_ERR_INVALID_ARG;
     if (rows * n == 0) return PFHE_OK;
     if (!a || !out) return PFHE_ERR_INVALID_ARG;
     if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
@@ -431,7 +439,7 @@ template <typename T, typename D> static pfhe_status dcrt_host_transform(const D
 template <typename T>
 static pfhe_status slice_op_host(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
                                  size_t n) {
-    if (op < 0 || op > PFHE_OP_SUB_FACTOR_MUL) return PFHE_ERR_INVALID_ARG;
+    if (op < 0 || op > PFHE_OP_REDUCE_LAZY) return PFHE_ERR_INVALID_ARG;
     if (rows * n == 0) return PFHE_OK;
     if (!a || !out) return PFHE_ERR_INVALID_ARG;
     if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
@@ -515,13 +523,13 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     T pfhe_ntt##B##_inv_root(const pfhe_ntt##B *t) { return t ? t->h.inv_root : 0; }                                                  \
     T pfhe_ntt##B##_inv_n(const pfhe_ntt##B *t) { return t ? t->h.inv_n : 0; }                                                        \
     int pfhe_ntt##B##_device(const pfhe_ntt##B *t) { return t ? t->device : -1; }                                                     \
-    pfhe_status pfhe_ntt##B##_transform_slice(const pfhe_ntt##B *t, T *poly, int) { return host_transform<T>(t, poly, 1, true); }     \
-    pfhe_status pfhe_ntt##B##_inverse_transform_slice(const pfhe_ntt##B *t, T *v, int) { return host_transform<T>(t, v, 1, false); }  \
-    pfhe_status pfhe_ntt##B##_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int) {                                       \
-        return host_transform<T>(t, p, batch, true);                                                                                  \
+    pfhe_status pfhe_ntt##B##_transform_slice(const pfhe_ntt##B *t, T *poly, int lazy) { return host_transform<T>(t, poly, 1, true, lazy != 0); }     \
+    pfhe_status pfhe_ntt##B##_inverse_transform_slice(const pfhe_ntt##B *t, T *v, int lazy) { return host_transform<T>(t, v, 1, false, lazy != 0); }  \
+    pfhe_status pfhe_ntt##B##_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int lazy) {                                  \
+        return host_transform<T>(t, p, batch, true, lazy != 0);                                                                                \
     }                                                                                                                                 \
-    pfhe_status pfhe_ntt##B##_inverse_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int) {                               \
-        return host_transform<T>(t, p, batch, false);                                                                                 \
+    pfhe_status pfhe_ntt##B##_inverse_transform_slices(const pfhe_ntt##B *t, T *p, size_t batch, int lazy) {                          \
+        return host_transform<T>(t, p, batch, false, lazy != 0);                                                                                \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_transform_monomial(const pfhe_ntt##B *t, T coeff, size_t degree, T *values) {                           \
         return host_monomial<T>(t, coeff, degree, values);                                                                            \

@@ -9,6 +9,8 @@
 //
 // One polynomial per thread group (TPP threads); a CTA carries PPB groups. Each polynomial is read from
 // HBM once and written once; everything in between lives in registers / shared memory.
+#include <cstdlib>
+
 #include "internal.hpp"
 #include "host_math.hpp"
 
@@ -17,6 +19,10 @@ namespace pfhe {
 std::atomic<uint64_t> g_launches{0};
 
 int choose_loge(int bits, int log_n) {
+    if (bits == 64 && log_n == 12) {  // experiment hook (tuning only): PFHE_LOGE12=3|4|5
+        const char *e = getenv("PFHE_LOGE12");
+        if (e && e[0] >= '3' && e[0] <= '5') return e[0] - '0';
+    }
     if (bits == 64) {
         switch (log_n) {
             case 10: return 5;
@@ -337,7 +343,14 @@ cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint6
         switch (tb0.log_n) {
             case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 11: return run_ntt<T, 11, 4, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-            case 12: return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 12:
+                if (tb0.loge == 3) return run_ntt<T, 12, 3, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+                if (tb0.loge == 5) {
+                    const char *e = getenv("PFHE_PPB12");
+                    if (e && e[0] == '2') return run_ntt<T, 12, 5, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+                    return run_ntt<T, 12, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+                }
+                return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 13: return run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 14: return run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
         }

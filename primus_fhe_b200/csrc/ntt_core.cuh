@@ -133,12 +133,15 @@ struct F64Field {
     using Tw = double;
     struct Ctx {
         double q, qinv, inv_n;
+        double off1, off2;  // 2^52 + q, 2^52 + 2q (exact): biases that make a lazy value a positive 52-bit mantissa
+        uint64_t qi;
         uint32_t q_hi, q_lo;
     };
     static constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
     static constexpr double kTwo52 = 4503599627370496.0;
     __device__ __forceinline__ static Ctx ctx(const DevNtt<uint64_t> &tb) {
-        return Ctx{tb.q_f, tb.qinv_f, tb.inv_n_f, (uint32_t)__double2hiint(tb.q_f), (uint32_t)__double2loint(tb.q_f)};
+        return Ctx{tb.q_f, tb.qinv_f, tb.inv_n_f, kTwo52 + tb.q_f, kTwo52 + 2.0 * tb.q_f, tb.q,
+                   (uint32_t)__double2hiint(tb.q_f), (uint32_t)__double2loint(tb.q_f)};
     }
     __device__ __forceinline__ static const Tw *fwd_tw(const DevNtt<uint64_t> &tb) { return tb.fwd_pass_f; }
     __device__ __forceinline__ static const Tw *inv_tw(const DevNtt<uint64_t> &tb) { return tb.inv_pass_f; }
@@ -170,13 +173,8 @@ struct F64Field {
         const double t = __dadd_rn(v, kTwo52);
         return ((uint64_t)((uint32_t)__double2hiint(t) & 0x000fffffu) << 32) | (uint32_t)__double2loint(t);
     }
-    // inputs may be lazy (< 4q forward, < 2q inverse): bring to [0, 2q) / fold
-    __device__ __forceinline__ static Elem load(uint64_t w, const Ctx &c) {
-        double v = from_u64(w);
-        const double two_q = __dadd_rn(c.q, c.q);
-        if (v >= two_q) v = __dsub_rn(v, two_q);
-        return fold(v, c);
-    }
+    // inputs are canonical words in [0, q) (lazy-range callers are canonicalised by a pointwise pre-pass, capi.cu)
+    __device__ __forceinline__ static Elem load(uint64_t w, const Ctx &) { return from_u64(w); }
     __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &c) { return load((uint64_t)__double_as_longlong(raw), c); }
     // |x|,|y| < 2q on entry and exit
     __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
@@ -196,13 +194,19 @@ struct F64Field {
         x = mulmod(s, c.inv_n, c);
         y = mulmod(d, w, c);
     }
-    __device__ __forceinline__ static uint64_t canon(double v, const Ctx &c) {  // (-q, q) -> [0, q)
-        if (v < 0.0) v = __dadd_rn(v, c.q);
-        return to_u64(v);
+    // canonical words: one biased FP64 add exposes v + kq as a 52-bit integer mantissa; the final conditional
+    // subtractions run on the integer ALU (keeps the FP64 pipe, the bottleneck, for butterflies)
+    __device__ __forceinline__ static uint64_t mant(double t) {
+        return ((uint64_t)((uint32_t)__double2hiint(t) & 0x000fffffu) << 32) | (uint32_t)__double2loint(t);
     }
-    __device__ __forceinline__ static uint64_t fwd_word(Elem v, const Ctx &c) { return canon(fold(v, c), c); }
+    __device__ __forceinline__ static uint64_t fwd_word(Elem v, const Ctx &c) {  // v in (-2q, 2q)
+        const uint64_t w = mant(__dadd_rn(v, c.off2));                           // v + 2q in (0, 4q)
+        return csub<uint64_t>(csub<uint64_t>(w, c.qi + c.qi), c.qi);
+    }
     __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)fwd_word(v, c)); }
-    __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) { return canon(v, c); }
+    __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) {  // v in (-q, q)
+        return csub<uint64_t>(mant(__dadd_rn(v, c.off1)), c.qi);
+    }
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return mulmod(fold(a, c), fold(b, c), c); }
 };
 

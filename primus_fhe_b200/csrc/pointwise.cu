@@ -41,6 +41,7 @@ __device__ __forceinline__ T apply_op(const Barrett<T> &br, T s, T sq, T a, T b,
         case PFHE_OP_FACTOR_MUL: return shoup<T>(a, s, sq, q);
         case PFHE_OP_ADD_FACTOR_MUL: return mod_add<T>(o, shoup<T>(a, s, sq, q), q);
         case PFHE_OP_SUB_FACTOR_MUL: return mod_sub<T>(o, shoup<T>(a, s, sq, q), q);
+        case PFHE_OP_REDUCE_LAZY: return csub<T>(csub<T>(a, q + q), q);
     }
     return 0;
 }
@@ -119,6 +120,7 @@ cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T 
         PFHE_CASE(PFHE_OP_FACTOR_MUL)
         PFHE_CASE(PFHE_OP_ADD_FACTOR_MUL)
         PFHE_CASE(PFHE_OP_SUB_FACTOR_MUL)
+        PFHE_CASE(PFHE_OP_REDUCE_LAZY)
 #undef PFHE_CASE
     }
     return cudaErrorInvalidValue;
