@@ -57,41 +57,56 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons through NVML (in-process thread, ~2 ms period) while the timed
+    region runs; falls back to `nvidia-smi -lms` when NVML is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.stop_flag, self.thread, self.proc, self.mx = gpu_index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(p.strip().isdigit() for p in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((time.perf_counter(), float(clk), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        # keep only samples under load (clock above idle) when there are any
-        loaded = [c for c in sm if c > 0.5 * mx] or sm
-        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+    def stop(self, t_begin=None, t_end=None):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        rows = self.rows
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        note = "sampled inside the timed region"
+        if len(inside) < 3:
+            inside, note = rows, "timed region shorter than 3 samples: all samples of this run (warm-up + timed + e2e) used"
+        sm = [r[1] for r in inside]
+        reasons = set()
+        for r in inside:
+            for name, bit in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons),
+                "samples": len(sm), "note": note}
 
 
 def cpu_reference(sample_batch: int, reps: int):
@@ -148,7 +163,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (extra) measurements")
@@ -184,15 +199,16 @@ def main():
     data = torch.randint(0, Q, (batch, N), dtype=torch.int64, device="cuda", generator=g)
 
     # ---- device-resident throughput (value) --------------------------------------------------------
-    for _ in range(args.warmup):
-        table.forward_batch(data)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        table.forward_batch(data)
+    barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = P.launch_count()
     e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     e_all0.record()
     for a, b in evs:
         a.record()
@@ -200,10 +216,10 @@ def main():
         b.record()
     e_all1.record()
     barrier()
+    t_end = time.perf_counter()
     launches = P.launch_count() - launches0
     total_ms = e_all0.elapsed_time(e_all1)
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
-    clocks = sampler.stop() if rank == 0 else None
     t_ms = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -227,6 +243,7 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_batch * e2e_steps / float(t_e.item())
     del host
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     if rank != 0:
         if dist is not None:
