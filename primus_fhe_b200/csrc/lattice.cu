@@ -14,6 +14,8 @@
 // Blind rotation (composed; not in the reference): the accumulator (2 polynomials)
 // stays in shared memory for all n_lwe CMux steps; only the LWE sample, the test vector and the final
 // accumulator touch HBM; the bootstrapping key streams through L2.
+#include <cstdlib>
+
 #include "internal.hpp"
 
 namespace pfhe {
@@ -58,17 +60,17 @@ template <> struct AccOf<uint64_t> {
     __device__ __forceinline__ static void set(Wide2<uint64_t> &a, uint64_t v) { a.lo = v; a.hi = 0; }
 };
 
-// gadget digit of level `level` for value v (recomputes the carry chain from level 0; levels are few)
-template <typename T> __device__ __forceinline__ T gadget_digit(const GadgetParams<T> &g, T v, uint32_t level) {
+// init_value_carry (primus_decompose/src/primitive/basis.rs:254-283): adjusted value + initial carry
+template <typename T> __device__ __forceinline__ T gadget_init(const GadgetParams<T> &g, T v, uint32_t &carry) {
     if (g.has_threshold && v >= g.threshold) v += g.add;
-    uint32_t carry = g.has_init_mask ? (uint32_t)((v & g.init_mask) != 0) : 0u;
-    T d = 0;
-    for (uint32_t l = 0; l <= level; l++) {
-        const T t = ((v >> (g.drop_bits + l * g.log_basis)) & g.basis_m1) + carry;
-        carry = (t & g.carry_mask) != 0;
-        d = carry ? (t > g.basis_m1 ? T(0) : t + g.q_minus_basis) : t;
-    }
-    return d;
+    carry = g.has_init_mask ? (uint32_t)((v & g.init_mask) != 0) : 0u;
+    return v;
+}
+// OnceSignedDecomposer::decompose_to for level l (primitive/common.rs:246-259); updates the carry
+template <typename T> __device__ __forceinline__ T gadget_level(const GadgetParams<T> &g, T adj, uint32_t shift, uint32_t &carry) {
+    const T t = ((adj >> shift) & g.basis_m1) + carry;
+    carry = (t & g.carry_mask) != 0;
+    return carry ? (t > g.basis_m1 ? T(0) : t + g.q_minus_basis) : t;
 }
 
 // Vec loads through the read-only path
@@ -96,15 +98,23 @@ template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
         uint32_t terms = 0;
 #pragma unroll 1
         for (int r = 0; r < COMPS; r++) {
+            // adjusted coefficients and carries of this component stay in registers across the levels
+            T adj[E];
+            uint32_t carry[E];
+#pragma unroll
+            for (int j = 0; j < E; j++) adj[j] = gadget_init<T>(g, get(r, Core::elem_index(FB0, t, j)), carry[j]);
 #pragma unroll 1
             for (uint32_t l = 0; l < g.levels; l++) {
                 T x[E];
+                const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
-                for (int j = 0; j < E; j++) x[j] = gadget_digit<T>(g, get(r, Core::elem_index(FB0, t, j)), l);
-                Core::template fwd_from<0>(x, sm, tb, cx, t, sync);
+                for (int j = 0; j < E; j++) x[j] = gadget_level<T>(g, adj[j], shift, carry[j]);
+                int tt = t;  // opaque copy: keeps per-pass address arithmetic inside the loop instead of ~60 hoisted registers
+                asm volatile("" : "+r"(tt));
+                Core::template fwd_from<0>(x, sm, tb, cx, tt, sync);
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = csub(csub(x[j], two_q), q);
-                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)tt * E;
                 if (terms == 16) {  // keep the lazy double-word sums below 2^(2*BITS)
 #pragma unroll
                     for (int c = 0; c < COMPS; c++)
@@ -174,8 +184,8 @@ external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_const
 }
 
 // Blind rotation: one ciphertext per thread group, accumulator resident in shared memory.
-template <typename T, int LOGN, int LOGE, int PPB>
-__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+template <typename T, int LOGN, int LOGE, int PPB, int MINB>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, MINB)
 blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant__ GadgetParams<T> g, const T *__restrict__ bsk,
                     uint32_t n_lwe, const uint32_t *__restrict__ lwe, const T *__restrict__ test_vector, T *__restrict__ acc_out,
                     size_t batch) {
@@ -261,12 +271,12 @@ static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T
     count_launch();
     return cudaGetLastError();
 }
-template <typename T, int LOGN, int LOGE, int PPB>
+template <typename T, int LOGN, int LOGE, int PPB, int MINB = 1>
 static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe, const uint32_t *lwe,
                           const T *tv, T *acc_out, size_t batch, cudaStream_t stream) {
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * 3 * ((size_t)1 << LOGN);
-    auto k = blind_rotate_kernel<T, LOGN, LOGE, PPB>;
+    auto k = blind_rotate_kernel<T, LOGN, LOGE, PPB, MINB>;
     cudaError_t e;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch);
@@ -278,7 +288,7 @@ static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T
 // out for lattice_loge(bits, log_n) -- capi.cu passes the matching DevNtt view.
 int lattice_loge(int bits, int log_n) {
     if (log_n < 10 || log_n > 12) return 0;
-    return bits == 64 ? 3 : 4;
+    return 3;
 }
 
 #define PFHE_EP_CASE(LOGN, LOGE, PPB)                                                                          \
@@ -305,9 +315,9 @@ cudaError_t launch_external_product<uint32_t>(const DevNtt<uint32_t> &tb, const 
     using T = uint32_t;
     if (batch == 0) return cudaSuccess;
     switch (tb.log_n) {
-        PFHE_EP_CASE(10, 4, 2)
-        PFHE_EP_CASE(11, 4, 2)
-        PFHE_EP_CASE(12, 4, 1)
+        PFHE_EP_CASE(10, 3, 1)
+        PFHE_EP_CASE(11, 3, 1)
+        PFHE_EP_CASE(12, 3, 1)
     }
     return cudaErrorNotSupported;
 }
@@ -330,9 +340,16 @@ cudaError_t launch_blind_rotate<uint32_t>(const DevNtt<uint32_t> &tb, const Gadg
     using T = uint32_t;
     if (batch == 0) return cudaSuccess;
     switch (tb.log_n) {
-        case 10: return run_br<T, 10, 4, 2>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
-        case 11: return run_br<T, 11, 4, 2>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
-        case 12: return run_br<T, 12, 4, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 10: {
+            const char *e = getenv("PFHE_BR_MINB");  // tuning hook
+            const int mb = e ? atoi(e) : 4;
+            if (mb == 5) return run_br<T, 10, 3, 1, 5>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+            if (mb == 8) return run_br<T, 10, 3, 1, 8>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+            if (mb == 6) return run_br<T, 10, 3, 1, 6>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+            return run_br<T, 10, 3, 1, 4>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        }
+        case 11: return run_br<T, 11, 3, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
+        case 12: return run_br<T, 12, 3, 1>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, s);
     }
     return cudaErrorNotSupported;
 }

@@ -25,8 +25,10 @@ template <> struct Word<uint64_t> {
 __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 __device__ __forceinline__ uint64_t mulhi(uint64_t a, uint64_t b) { return __umul64hi(a, b); }
 
-// x mod m for x < 2m
+// x mod m for x < 2m.  u32: the reference's wrapping-min trick (one IADD + one VIMNMX,
+// primus_ntt/src/ntt/prime32/scalar/arithmetic.rs:3-6); u64: compare/select (a 64-bit min is no cheaper).
 template <typename T> __device__ __forceinline__ T csub(T x, T m) { return x >= m ? x - m : x; }
+template <> __device__ __forceinline__ uint32_t csub<uint32_t>(uint32_t x, uint32_t m) { return min(x, x - m); }
 
 // Shoup lazy product: w*y - q*floor(w'*y / 2^BITS)  in [0, 2q), any word-sized y.
 template <typename T> __device__ __forceinline__ T shoup_lazy(T y, T w, T wq, T q) {
