@@ -46,13 +46,19 @@ struct DeviceGuard {
 };
 
 // per-thread copy streams (thread safe by construction)
-constexpr int kPipe = 3;
+constexpr int kPipe = 4;  // pipeline depth of the host-slice shims (H2D / kernel / D2H + one slack stage)
 struct ThreadStreams {
     std::vector<std::vector<cudaStream_t>> per_device;
     cudaError_t get(int device, cudaStream_t *out) {
         if ((int)per_device.size() <= device) per_device.resize(device + 1);
         auto &v = per_device[device];
         if (v.empty()) {
+            // keep freed staging buffers in the stream-ordered pool instead of returning them to the driver at every sync
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
             v.resize(kPipe);
             for (auto &s : v) {
                 cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -136,7 +142,7 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     const auto &h = hd->h;
     const size_t n = h.n;
     std::vector<Pair> fwd(n), inv(n), fp, ip, fpl, ipl;
-    std::vector<double> fpf, ipf;
+    std::vector<double> fpf, ipf, fplf, iplf;
     for (size_t k = 0; k < n; k++) {
         fwd[k].x = h.roots[k];
         fwd[k].y = h.roots_q[k];
@@ -159,13 +165,23 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
             ipf[i] = (double)ip[i].x;
         }
     }
+    const bool use_f64_lat = BITS == 64 && loge_lat != 0 && ((uint64_t)q >> 50) == 0 && !(no_f64 && no_f64[0] == '1');
+    if (use_f64_lat) {
+        fplf.resize(fpl.size());
+        iplf.resize(ipl.size());
+        for (size_t i = 0; i < fpl.size(); i++) {
+            fplf[i] = (double)fpl[i].x;
+            iplf[i] = (double)ipl[i].x;
+        }
+    }
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t sz_pair = sizeof(Pair);
     size_t off_fwd = 0, off_inv = align(off_fwd + n * sz_pair), off_fp = align(off_inv + n * sz_pair),
            off_ip = align(off_fp + fp.size() * sz_pair), off_fpl = align(off_ip + ip.size() * sz_pair),
            off_ipl = align(off_fpl + fpl.size() * sz_pair), off_ord = align(off_ipl + ipl.size() * sz_pair),
            off_fpf = align(off_ord + 2 * n * sizeof(T)), off_ipf = align(off_fpf + fpf.size() * sizeof(double)),
-           total = align(off_ipf + ipf.size() * sizeof(double));
+           off_fplf = align(off_ipf + ipf.size() * sizeof(double)), off_iplf = align(off_fplf + fplf.size() * sizeof(double)),
+           total = align(off_iplf + iplf.size() * sizeof(double));
     std::vector<unsigned char> stage(total, 0);
     memcpy(stage.data() + off_fwd, fwd.data(), n * sz_pair);
     memcpy(stage.data() + off_inv, inv.data(), n * sz_pair);
@@ -176,6 +192,8 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     memcpy(stage.data() + off_ord, h.ordinal.data(), 2 * n * sizeof(T));
     if (!fpf.empty()) memcpy(stage.data() + off_fpf, fpf.data(), fpf.size() * sizeof(double));
     if (!ipf.empty()) memcpy(stage.data() + off_ipf, ipf.data(), ipf.size() * sizeof(double));
+    if (!fplf.empty()) memcpy(stage.data() + off_fplf, fplf.data(), fplf.size() * sizeof(double));
+    if (!iplf.empty()) memcpy(stage.data() + off_iplf, iplf.data(), iplf.size() * sizeof(double));
     cudaError_t e = cudaMalloc(&hd->blob, total);
     if (e == cudaSuccess) e = cudaMemcpy(hd->blob, stage.data(), total, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -207,7 +225,9 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     hd->dev = d;
     hd->dev_lat = d;
     hd->dev_lat.loge = (uint32_t)loge_lat;
-    hd->dev_lat.use_f64 = 0;
+    hd->dev_lat.use_f64 = use_f64_lat ? 1u : 0u;
+    hd->dev_lat.fwd_pass_f = reinterpret_cast<const double *>(base + off_fplf);
+    hd->dev_lat.inv_pass_f = reinterpret_cast<const double *>(base + off_iplf);
     hd->dev_lat.fwd_pass = reinterpret_cast<const Pair *>(base + off_fpl);
     hd->dev_lat.inv_pass = reinterpret_cast<const Pair *>(base + off_ipl);
     *out = hd;
@@ -240,12 +260,17 @@ static pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
     PFHE_CUDA(t_streams.get(device, st));
     size_t per_unit = out_alias >= 0 ? 0 : out_bytes;  // out_alias: the kernel updates input region #out_alias in place
     for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];
-    // chunk so that each stage moves ~16 MiB; at least one unit
-    size_t chunk = (size_t)(16u << 20) / (per_unit ? per_unit : 1);
+    // chunk so that each stage moves ~64 MiB (measured best on PCIe Gen5; PFHE_PIPE_CHUNK_MB overrides); at least one unit
+    size_t chunk_bytes = (size_t)64 << 20;
+    if (const char *e = getenv("PFHE_PIPE_CHUNK_MB")) {
+        const long mb = atol(e);
+        if (mb > 0 && mb <= 1024) chunk_bytes = (size_t)mb << 20;
+    }
+    size_t chunk = chunk_bytes / (per_unit ? per_unit : 1);
     if (chunk == 0) chunk = 1;
     if (chunk > units) chunk = units;
     const int nbuf = (int)((units + chunk - 1) / chunk < (size_t)kPipe ? (units + chunk - 1) / chunk : kPipe);
-    void *dbuf[kPipe] = {nullptr, nullptr, nullptr};
+    void *dbuf[kPipe] = {};
     pfhe_status status = PFHE_OK;
     for (int i = 0; i < nbuf; i++) {
         cudaError_t e = cudaMallocAsync(&dbuf[i], chunk * per_unit, st[i]);

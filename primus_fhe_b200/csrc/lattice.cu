@@ -42,22 +42,43 @@ __device__ __forceinline__ void mac_wide(Wide2<uint64_t> &acc, uint64_t a, uint6
     acc.lo += lo;
     acc.hi += hi + (acc.lo < lo);
 }
-template <typename T> struct AccOf;
-template <> struct AccOf<uint32_t> {
-    using type = uint64_t;
-    __device__ __forceinline__ static uint32_t reduce(const Barrett<uint32_t> &br, uint64_t a) {
-        return barrett_reduce_wide(br, (uint32_t)a, (uint32_t)(a >> 32));
-    }
-    __device__ __forceinline__ static void zero(uint64_t &a) { a = 0; }
-    __device__ __forceinline__ static void set(uint64_t &a, uint32_t v) { a = v; }
+
+// Key multiply-accumulate policy per field.
+//  integer pipe: lazy double-word sums, <= 16 products before one Barrett reduction (reduce_dot_product,
+//                primus_modulus/src/common/compact/slice.rs:371-401; safe because q < 2^(BITS-2));
+//  FP64 pipe   : acc <- fold(acc + mulmod(x, key)) with everything an exact integer double in (-q, q).
+template <typename F> struct LatAcc;
+template <> struct LatAcc<IntField<uint32_t>> {
+    using F = IntField<uint32_t>;
+    using Acc = uint64_t;
+    static constexpr bool kRenorm = true;
+    __device__ __forceinline__ static void zero(Acc &a) { a = 0; }
+    __device__ __forceinline__ static uint32_t prepare(uint32_t x, const F::Ctx &c) { return F::fwd_word(x, c); }
+    __device__ __forceinline__ static void mac(Acc &a, uint32_t x, uint32_t key, const F::Ctx &) { mac_wide(a, x, key); }
+    __device__ __forceinline__ static void renorm(Acc &a, const F::Ctx &c) { a = barrett_reduce_wide(c.br, (uint32_t)a, (uint32_t)(a >> 32)); }
+    __device__ __forceinline__ static uint32_t final(const Acc &a, const F::Ctx &c) { return barrett_reduce_wide(c.br, (uint32_t)a, (uint32_t)(a >> 32)); }
 };
-template <> struct AccOf<uint64_t> {
-    using type = Wide2<uint64_t>;
-    __device__ __forceinline__ static uint64_t reduce(const Barrett<uint64_t> &br, const Wide2<uint64_t> &a) {
-        return barrett_reduce_wide(br, a.lo, a.hi);
+template <> struct LatAcc<IntField<uint64_t>> {
+    using F = IntField<uint64_t>;
+    using Acc = Wide2<uint64_t>;
+    static constexpr bool kRenorm = true;
+    __device__ __forceinline__ static void zero(Acc &a) { a.lo = 0; a.hi = 0; }
+    __device__ __forceinline__ static uint64_t prepare(uint64_t x, const F::Ctx &c) { return F::fwd_word(x, c); }
+    __device__ __forceinline__ static void mac(Acc &a, uint64_t x, uint64_t key, const F::Ctx &) { mac_wide(a, x, key); }
+    __device__ __forceinline__ static void renorm(Acc &a, const F::Ctx &c) { a.lo = barrett_reduce_wide(c.br, a.lo, a.hi); a.hi = 0; }
+    __device__ __forceinline__ static uint64_t final(const Acc &a, const F::Ctx &c) { return barrett_reduce_wide(c.br, a.lo, a.hi); }
+};
+template <> struct LatAcc<F64Field> {
+    using F = F64Field;
+    using Acc = double;
+    static constexpr bool kRenorm = false;
+    __device__ __forceinline__ static void zero(Acc &a) { a = 0.0; }
+    __device__ __forceinline__ static double prepare(double x, const F::Ctx &) { return x; }  // |x| < 2q is a valid multiplier input
+    __device__ __forceinline__ static void mac(Acc &a, double x, uint64_t key, const F::Ctx &c) {
+        a = F::fold(__dadd_rn(a, F::mulmod(x, F::from_u64(key), c)), c);
     }
-    __device__ __forceinline__ static void zero(Wide2<uint64_t> &a) { a.lo = 0; a.hi = 0; }
-    __device__ __forceinline__ static void set(Wide2<uint64_t> &a, uint64_t v) { a.lo = v; a.hi = 0; }
+    __device__ __forceinline__ static void renorm(Acc &, const F::Ctx &) {}
+    __device__ __forceinline__ static double final(const Acc &a, const F::Ctx &) { return a; }  // (-q, q): inverse-transform input
 };
 
 // init_value_carry (primus_decompose/src/primitive/basis.rs:254-283): adjusted value + initial carry
@@ -82,19 +103,19 @@ template <typename V> __device__ __forceinline__ V ldg_vec(const V *p) {
     return v;
 }
 
-template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
-    using F = IntField<T>;
+template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
     using Core = NttCore<F, LOGN, LOGE>;
-    using Acc = typename AccOf<T>::type;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    using LA = LatAcc<F>;
+    using Acc = typename LA::Acc;
     static constexpr int N = Core::N, E = Core::E, TPP = Core::TPP, FB0 = Core::P::fb(0);
     static constexpr int CW = Core::CW, NV = Core::NV;
 
     // acc[c][j] (+)= sum_{r,l} fwd(digit_l(get(r, idx))) * key[r][l][c][t*E + j]
     template <typename GetIn, typename SyncF>
     __device__ __forceinline__ static void accumulate(GetIn get, const T *__restrict__ key, const GadgetParams<T> &g, const DevNtt<T> &tb,
-                                                      Acc (&acc)[COMPS][E], T *sm, int t, SyncF sync) {
-        const T q = tb.q, two_q = tb.two_q;
-        const typename F::Ctx cx = F::ctx(tb);
+                                                      const typename F::Ctx &cx, Acc (&acc)[COMPS][E], Elem *sm, int t, SyncF sync) {
         uint32_t terms = 0;
 #pragma unroll 1
         for (int r = 0; r < COMPS; r++) {
@@ -105,31 +126,31 @@ template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
             for (int j = 0; j < E; j++) adj[j] = gadget_init<T>(g, get(r, Core::elem_index(FB0, t, j)), carry[j]);
 #pragma unroll 1
             for (uint32_t l = 0; l < g.levels; l++) {
-                T x[E];
+                Elem x[E];
                 const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
-                for (int j = 0; j < E; j++) x[j] = gadget_level<T>(g, adj[j], shift, carry[j]);
-                int tt = t;  // opaque copy: keeps per-pass address arithmetic inside the loop instead of ~60 hoisted registers
-                asm volatile("" : "+r"(tt));
-                Core::template fwd_from<0>(x, sm, tb, cx, tt, sync);
+                for (int j = 0; j < E; j++) x[j] = F::load(gadget_level<T>(g, adj[j], shift, carry[j]), cx);
+                Core::template fwd_from<0>(x, sm, tb, cx, t, sync);
 #pragma unroll
-                for (int j = 0; j < E; j++) x[j] = csub(csub(x[j], two_q), q);
-                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)tt * E;
-                if (terms == 16) {  // keep the lazy double-word sums below 2^(2*BITS)
+                for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
+                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+                if (LA::kRenorm) {
+                    if (terms == 16) {  // keep the lazy double-word sums below 2^(2*BITS)
 #pragma unroll
-                    for (int c = 0; c < COMPS; c++)
+                        for (int c = 0; c < COMPS; c++)
 #pragma unroll
-                        for (int j = 0; j < E; j++) AccOf<T>::set(acc[c][j], AccOf<T>::reduce(tb.br, acc[c][j]));
-                    terms = 1;
+                            for (int j = 0; j < E; j++) LA::renorm(acc[c][j], cx);
+                        terms = 1;
+                    }
+                    terms++;
                 }
-                terms++;
 #pragma unroll
                 for (int c = 0; c < COMPS; c++) {
 #pragma unroll
                     for (int v = 0; v < NV; v++) {
-                        const typename Core::Vec kv = ldg_vec(reinterpret_cast<const typename Core::Vec *>(kp + (size_t)c * N) + v);
+                        const typename Core::WVec kv = ldg_vec(reinterpret_cast<const typename Core::WVec *>(kp + (size_t)c * N) + v);
 #pragma unroll
-                        for (int w = 0; w < CW; w++) mac_wide(acc[c][v * CW + w], x[v * CW + w], kv.v[w]);
+                        for (int w = 0; w < CW; w++) LA::mac(acc[c][v * CW + w], x[v * CW + w], kv.v[w], cx);
                     }
                 }
             }
@@ -137,16 +158,20 @@ template <typename T, int LOGN, int LOGE, int COMPS> struct ExtProd {
     }
 };
 
-template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
+template <typename F, int LOGN, int LOGE, int COMPS, int PPB>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
-external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant__ GadgetParams<T> g, const T *__restrict__ key,
-                        const T *__restrict__ in, T *__restrict__ out, size_t batch, int to_coeff) {
-    using EP = ExtProd<T, LOGN, LOGE, COMPS>;
+external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, const __grid_constant__ GadgetParams<typename F::WordT> g,
+                        const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ in,
+                        typename F::WordT *__restrict__ out, size_t batch, int to_coeff) {
+    using EP = ExtProd<F, LOGN, LOGE, COMPS>;
     using Core = typename EP::Core;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    using LA = LatAcc<F>;
     constexpr int N = EP::N, E = EP::E, TPP = EP::TPP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
-    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * N;
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw) + (size_t)grp * N;
     size_t ct = (size_t)blockIdx.x * PPB + grp;
     const bool active = ct < batch;
     if (!active) {
@@ -154,27 +179,28 @@ external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_const
         ct = batch - 1;
     }
     typename LSyncFor<TPP>::type sync;
+    const typename F::Ctx cx = F::ctx(tb);
     const T *cin = in + ct * COMPS * N;
     T *cout = out + ct * COMPS * N;
     typename EP::Acc acc[COMPS][E];
 #pragma unroll
     for (int c = 0; c < COMPS; c++)
 #pragma unroll
-        for (int j = 0; j < E; j++) AccOf<T>::zero(acc[c][j]);
-    EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, acc, sm, t, sync);
+        for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
+    EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync);
 #pragma unroll
     for (int c = 0; c < COMPS; c++) {
-        T x[E];
-#pragma unroll
-        for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
+        Elem x[E];
         if (to_coeff) {
-            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, EP::F::ctx(tb), t, sync);
-            if (active) {
 #pragma unroll
-                for (int j = 0; j < E; j++) cout[(size_t)c * N + Core::elem_index(EP::FB0, t, j)] = x[j];
-            }
+            for (int j = 0; j < E; j++) x[j] = F::from_mac(LA::final(acc[c][j], cx), cx);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, cx, t, sync);
+            if (active) Core::inv_regs_to_global(x, cout + (size_t)c * N, cx, t);
             sync();
         } else {
+            // NTT-domain output: canonical words, bit-reversed order, coalesced through the buffer
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::mac_bits(LA::final(acc[c][j], cx), cx);
             if (active) Core::template sm_store<Core::P::NPASS - 1>(x, sm, t);
             sync();
             if (active) Core::copy_s2g(sm, cout + (size_t)c * N, t);
@@ -183,19 +209,22 @@ external_product_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_const
     }
 }
 
-// Blind rotation: one ciphertext per thread group, accumulator resident in shared memory.
-template <typename T, int LOGN, int LOGE, int PPB, int MINB>
+// Blind rotation: one ciphertext per thread group, accumulator resident in shared memory (canonical words).
+template <typename F, int LOGN, int LOGE, int PPB, int MINB>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, MINB)
-blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant__ GadgetParams<T> g, const T *__restrict__ bsk,
-                    uint32_t n_lwe, const uint32_t *__restrict__ lwe, const T *__restrict__ test_vector, T *__restrict__ acc_out,
-                    size_t batch) {
-    using EP = ExtProd<T, LOGN, LOGE, 2>;
+blind_rotate_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, const __grid_constant__ GadgetParams<typename F::WordT> g,
+                    const typename F::WordT *__restrict__ bsk, uint32_t n_lwe, const uint32_t *__restrict__ lwe,
+                    const typename F::WordT *__restrict__ test_vector, typename F::WordT *__restrict__ acc_out, size_t batch) {
+    using EP = ExtProd<F, LOGN, LOGE, 2>;
     using Core = typename EP::Core;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    using LA = LatAcc<F>;
     constexpr int N = EP::N, E = EP::E, TPP = EP::TPP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
-    T *sm = reinterpret_cast<T *>(smem_raw) + (size_t)grp * 3 * N;  // exchange buffer
-    T *accs = sm + N;                                               // ACC: [2][N], natural order
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw) + (size_t)grp * 3 * N;  // exchange buffer
+    T *accs = reinterpret_cast<T *>(sm + N);                              // ACC: [2][N] canonical words, natural order
     size_t ct = (size_t)blockIdx.x * PPB + grp;
     const bool active = ct < batch;
     if (!active) {
@@ -203,6 +232,7 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
         ct = batch - 1;
     }
     typename LSyncFor<TPP>::type sync;
+    const typename F::Ctx cx = F::ctx(tb);
     const T q = tb.q;
     const uint32_t *my_lwe = lwe + ct * (size_t)(n_lwe + 1);
     const uint32_t two_n_mask = 2 * N - 1;
@@ -212,8 +242,7 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
         const uint32_t rot = (2 * N - b) & two_n_mask;
         for (int i = t; i < N; i += TPP) {
             accs[i] = 0;
-            // out[i] = sign * tv[(i - rot) mod 2N]
-            const uint32_t srcw = ((uint32_t)i - rot) & two_n_mask;
+            const uint32_t srcw = ((uint32_t)i - rot) & two_n_mask;  // out[i] = sign * tv[(i - rot) mod 2N]
             const T v = __ldg(test_vector + (srcw & (N - 1)));
             accs[N + i] = (srcw >= (uint32_t)N) ? mod_neg<T>(v, q) : v;
         }
@@ -227,7 +256,7 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 2; c++)
 #pragma unroll
-            for (int j = 0; j < E; j++) AccOf<T>::zero(acc[c][j]);
+            for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
         // D = ACC * X^a - ACC, evaluated on the fly from the resident accumulator
         auto getD = [&](int r, int idx) -> T {
             const T *p = accs + r * N;
@@ -236,18 +265,18 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
             const T rotated = (srcw >= (uint32_t)N) ? mod_neg<T>(v, q) : v;
             return mod_sub<T>(rotated, p[idx], q);
         };
-        EP::accumulate(getD, bsk + (size_t)i * rgsw_len, g, tb, acc, sm, t, sync);
+        EP::accumulate(getD, bsk + (size_t)i * rgsw_len, g, tb, cx, acc, sm, t, sync);
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            T x[E];
+            Elem x[E];
 #pragma unroll
-            for (int j = 0; j < E; j++) x[j] = AccOf<T>::reduce(tb.br, acc[c][j]);
-            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, EP::F::ctx(tb), t, sync);
+            for (int j = 0; j < E; j++) x[j] = F::from_mac(LA::final(acc[c][j], cx), cx);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, cx, t, sync);
             // ACC_c += result (each coefficient owned by exactly one thread)
 #pragma unroll
             for (int j = 0; j < E; j++) {
                 const int idx = Core::elem_index(EP::FB0, t, j);
-                accs[c * N + idx] = mod_add<T>(accs[c * N + idx], x[j], q);
+                accs[c * N + idx] = mod_add<T>(accs[c * N + idx], F::inv_word(x[j], cx), q);
             }
             sync();
         }
@@ -259,29 +288,50 @@ blind_rotate_kernel(const __grid_constant__ DevNtt<T> tb, const __grid_constant_
 }
 
 // ---- dispatch -------------------------------------------------------------------------------------
-template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
-static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
-                          cudaStream_t stream) {
+template <typename F, int LOGN, int LOGE, int COMPS, int PPB>
+static cudaError_t run_ep_f(const DevNtt<typename F::WordT> &tb, const GadgetParams<typename F::WordT> &g, const typename F::WordT *key,
+                            const typename F::WordT *in, typename F::WordT *out, size_t batch, bool to_coeff, cudaStream_t stream) {
+    using T = typename F::WordT;
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
-    auto k = external_product_kernel<T, LOGN, LOGE, COMPS, PPB>;
+    auto k = external_product_kernel<F, LOGN, LOGE, COMPS, PPB>;
     cudaError_t e;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
     count_launch();
     return cudaGetLastError();
 }
-template <typename T, int LOGN, int LOGE, int PPB, int MINB = 1>
-static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe, const uint32_t *lwe,
-                          const T *tv, T *acc_out, size_t batch, cudaStream_t stream) {
+template <typename F, int LOGN, int LOGE, int PPB, int MINB>
+static cudaError_t run_br_f(const DevNtt<typename F::WordT> &tb, const GadgetParams<typename F::WordT> &g, const typename F::WordT *bsk,
+                            uint32_t n_lwe, const uint32_t *lwe, const typename F::WordT *tv, typename F::WordT *acc_out, size_t batch,
+                            cudaStream_t stream) {
+    using T = typename F::WordT;
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * 3 * ((size_t)1 << LOGN);
-    auto k = blind_rotate_kernel<T, LOGN, LOGE, PPB, MINB>;
+    auto k = blind_rotate_kernel<F, LOGN, LOGE, PPB, MINB>;
     cudaError_t e;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch);
     count_launch();
     return cudaGetLastError();
+}
+
+
+template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
+static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
+                          cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (tb.use_f64) return run_ep_f<F64Field, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
+    }
+    return run_ep_f<IntField<T>, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
+}
+template <typename T, int LOGN, int LOGE, int PPB, int MINB = 1>
+static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe, const uint32_t *lwe, const T *tv,
+                          T *acc_out, size_t batch, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (tb.use_f64) return run_br_f<F64Field, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
+    }
+    return run_br_f<IntField<T>, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
 }
 
 // The lattice kernels use their own (smaller) register tile: DevNtt::fwd_pass/inv_pass must have been laid

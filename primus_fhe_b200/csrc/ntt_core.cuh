@@ -120,6 +120,9 @@ template <typename T> struct IntField {
     __device__ __forceinline__ static T inv_word(Elem v, const Ctx &) { return v; }
     // forward outputs a, b -> a*b mod q as an inverse-transform input (BarrettModulus::reduce_mul)
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return barrett_mul<T>(c.br, fwd_word(a, c), fwd_word(b, c)); }
+    // key-MAC results (canonical words here) as inverse-transform inputs / as canonical output bits
+    __device__ __forceinline__ static Elem from_mac(T v, const Ctx &) { return v; }
+    __device__ __forceinline__ static Elem mac_bits(T v, const Ctx &) { return v; }
 };
 
 // FP64 pipe (B200 keeps full-rate FP64: 64 DFMA/clk/SM, while a 64x64-bit integer product costs ~4 half-rate
@@ -208,6 +211,9 @@ struct F64Field {
         return csub<uint64_t>(mant(__dadd_rn(v, c.off1)), c.qi);
     }
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return mulmod(fold(a, c), fold(b, c), c); }
+    // key-MAC results (doubles in (-q, q)) as inverse-transform inputs / as canonical output bits
+    __device__ __forceinline__ static Elem from_mac(double v, const Ctx &) { return v; }
+    __device__ __forceinline__ static Elem mac_bits(double v, const Ctx &c) { return __longlong_as_double((long long)inv_word(v, c)); }
 };
 
 template <typename F, int LOGN, int LOGE> struct NttCore {
