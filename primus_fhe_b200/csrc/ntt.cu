@@ -10,6 +10,7 @@
 // One polynomial per thread group (TPP threads); a CTA carries PPB groups. Each polynomial is read from
 // HBM once and written once; everything in between lives in registers / shared memory.
 #include <cstdlib>
+#include <type_traits>
 
 #include "internal.hpp"
 #include "host_math.hpp"
@@ -65,8 +66,23 @@ template <typename T> __device__ __forceinline__ DevNtt<T> pick_table(const DevN
 // ------------------------------------------------------------------------------------------------
 // register-pass kernels (F = IntField<T> or F64Field)
 // ------------------------------------------------------------------------------------------------
+// occupancy targets (CTAs per SM) for the register allocator, per configuration
+template <typename F, int LOGN, int LOGE, int PPB> constexpr int ntt_min_blocks() {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    if (sizeof(typename F::WordT) == 8 && LOGN == 12 && LOGE == 4 && PPB == 1)
+        return sizeof(typename F::Elem) == 8 && !std::is_integral<typename F::Elem>::value ? 4 : 3;  // FP64: 64 regs x 4 CTAs; int: 80 x 3
+    return threads >= 512 ? 1 : 512 / threads;  // at least 16 warps per SM: cap the allocator at 128 registers
+}
+
+// polymul holds two polynomials' tiles in registers: only ask for 16 warps/SM when 2 tiles + scratch fit in 128 registers
+template <typename F, int LOGN, int LOGE, int PPB> constexpr int polymul_min_blocks() {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    constexpr int need = 2 * (1 << LOGE) * (int)(sizeof(typename F::WordT) / 4) + 48;
+    return (need <= 128 && threads < 512) ? 512 / threads : 1;
+}
+
 template <typename F, int LOGN, int LOGE, int PPB, bool FWD>
-__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ntt_min_blocks<F, LOGN, LOGE, PPB>())
 ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
            const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
     using Core = NttCore<F, LOGN, LOGE>;
@@ -101,7 +117,7 @@ ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<t
 }
 
 template <typename F, int LOGN, int LOGE, int PPB>
-__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, polymul_min_blocks<F, LOGN, LOGE, PPB>())
 polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
                const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, typename F::WordT *__restrict__ cc,
                size_t npolys) {
