@@ -1,0 +1,477 @@
+// rns.cu -- RNS limb handling and the multi-limb (L > 1) gadget / external product, plus the remaining
+// element-wise helpers of the path.
+//
+// Replaces:
+//   RNSBase::{compose_multiple_values_to, decompose_big_uint_values_to}      primus_rns/src/base.rs:457-481, :609-673
+//   RNSBase::wrapping_decompose_small_values_scaled_add_to (fused)            primus_rns/src/base.rs:326-386, :739-756
+//   BigUintApproxSignedBasis init + unsigned levels + centred lift            primus_decompose/src/big_integer/basis.rs:326-367,
+//                                                                             big_integer/common.rs:83-141,275-325; base.rs:279-315
+//   DcrtGlwe::add_dcrt_glev_mul_crt_poly_assign / CrtGlwe::mul_dcrt_ggsw_to   primus_lattice/src/glwe/dcrt.rs:178-255, glwe/crt.rs:200-227
+//   Polynomial::mul_monomial_assign / CrtGlwe::mul_monic_monomial_assign      primus_poly/src/poly/mul.rs:74-99, primus_lattice/src/glwe/crt.rs:76-114
+//   reduce_dot_product                                                         primus_modulus/src/common/compact/slice.rs:371-401
+// The L > 1 external product is composed from kernels (digits -> DCRT NTT -> fused MAC -> INTT) with a
+// stream-ordered scratch buffer; the L = 1 case has the fully fused kernel in lattice.cu.
+#include "internal.hpp"
+#include "host_math.hpp"
+#include "rns.hpp"
+
+namespace pfhe {
+
+static unsigned grid_for(size_t items, int threads) {
+    size_t blocks = (items + threads - 1) / threads;
+    const size_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+template <typename T> struct WideOf;
+template <> struct WideOf<uint32_t> { using type = uint64_t; };
+template <> struct WideOf<uint64_t> { using type = unsigned __int128; };
+
+// ---- multiword helpers on little-endian word arrays (register / local arrays of kRnsMaxWords) ----------
+template <typename T> __device__ __forceinline__ bool big_ge(const T *a, const T *b, int len) {
+    for (int i = len - 1; i >= 0; i--)
+        if (a[i] != b[i]) return a[i] > b[i];
+    return true;
+}
+template <typename T> __device__ __forceinline__ void big_sub(T *a, const T *b, int len) {
+    T borrow = 0;
+    for (int i = 0; i < len; i++) {
+        const T bi = b[i], ai = a[i];
+        const T d = ai - bi - borrow;
+        borrow = (ai < bi) || (ai == bi && borrow) ? 1 : 0;
+        a[i] = d;
+    }
+}
+template <typename T> __device__ __forceinline__ void big_add(T *a, const T *b, int len) {
+    T carry = 0;
+    for (int i = 0; i < len; i++) {
+        const T s = a[i] + b[i], s2 = s + carry;
+        carry = (s < a[i]) || (s2 < s) ? 1 : 0;
+        a[i] = s2;
+    }
+}
+// acc += m * v, returns the carry word
+template <typename T> __device__ __forceinline__ T big_mul_add(const T *m, T v, T *acc, int len) {
+    using W = typename WideOf<T>::type;
+    T carry = 0;
+    for (int i = 0; i < len; i++) {
+        const W s = (W)m[i] * v + acc[i] + carry;
+        acc[i] = (T)s;
+        carry = (T)(s >> (sizeof(T) * 8));
+    }
+    return carry;
+}
+
+// compose_to (base.rs:609-636)
+template <typename T> __device__ __forceinline__ void rns_compose(const RnsDev<T> &r, const T *residues, T *value) {
+    for (int k = 0; k < r.value_len; k++) value[k] = 0;
+    for (int i = 0; i < r.limbs; i++) {
+        const T prod = shoup<T>(residues[i], r.inv_punct[i], r.inv_punct_q[i], r.q[i]);
+        const T carry = big_mul_add<T>(r.punct[i], prod, value, r.value_len);
+        if (carry != 0 || big_ge<T>(value, r.product, r.value_len)) big_sub<T>(value, r.product, r.value_len);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) rns_compose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
+                                                          T *__restrict__ big, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        T res[kRnsMaxLimbs], value[kRnsMaxWords];
+        for (int l = 0; l < r.limbs; l++) res[l] = residues[(size_t)l * count + i];
+        rns_compose<T>(r, res, value);
+        for (int k = 0; k < r.value_len; k++) big[i * r.value_len + k] = value[k];
+    }
+}
+// decompose_big_uint_values_to: value mod q_i by Horner over the words (base.rs:457-481)
+template <typename T>
+__global__ void __launch_bounds__(128) rns_decompose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ big,
+                                                            T *__restrict__ residues, size_t count) {
+    using W = typename WideOf<T>::type;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        for (int l = 0; l < r.limbs; l++) {
+            W rem = 0;
+            for (int k = r.value_len - 1; k >= 0; k--) rem = ((rem << (sizeof(T) * 8)) | big[i * r.value_len + k]) % r.q[l];
+            residues[(size_t)l * count + i] = (T)rem;
+        }
+    }
+}
+
+// residues[limbs][count] -> digits[levels][limbs][count]: compose, init_value_carry, unsigned digits, centred lift
+template <typename T>
+__global__ void __launch_bounds__(128) rns_gadget_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
+                                                         T *__restrict__ digits, size_t count, size_t polys, size_t in_stride,
+                                                         size_t out_stride) {
+    // `polys` independent CRT polynomials: residues + p*in_stride, digits + p*out_stride
+    constexpr int BITS = sizeof(T) * 8;
+    const size_t total = polys * count;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = gid / count, i = gid % count;
+        const T *res_in = residues + p * in_stride;
+        T *dig = digits + p * out_stride;
+        T res[kRnsMaxLimbs], value[kRnsMaxWords + 1];
+        for (int l = 0; l < r.limbs; l++) res[l] = res_in[(size_t)l * count + i];
+        rns_compose<T>(r, res, value);
+        value[r.value_len] = 0;
+        if (r.has_threshold && big_ge<T>(value, r.threshold, r.value_len)) big_add<T>(value, r.add, r.value_len);
+        uint32_t carry = r.has_init_mask ? (uint32_t)((value[r.init_index] & r.init_mask) != 0) : 0u;
+        const T bm1 = r.basis_m1, half = (T)((r.basis_m1 + 2) / 2);  // ceil(B/2)
+        for (uint32_t lv = 0; lv < r.levels; lv++) {
+            const uint32_t pos = r.drop_bits + lv * r.log_basis;
+            const int idx = pos / BITS, sh = pos % BITS;
+            T lower = value[idx] >> sh;
+            if (sh + (int)r.log_basis > BITS && idx + 1 < r.value_len) lower |= value[idx + 1] << (BITS - sh);
+            const T t = (lower & bm1) + carry;
+            carry = (t & r.carry_mask) != 0;
+            const T d = t & bm1;
+            for (int l = 0; l < r.limbs; l++)
+                dig[((size_t)lv * r.limbs + l) * count + i] = (r.basis_m1 == 1 || d < half) ? d : r.q[l] - (bm1 + 1) + d;
+        }
+    }
+}
+
+// out[ct][c][limb][i] = sum_{r,l} digits[ct][r][l][limb][i] * key[r][l][c][limb][i] mod q_limb  (NTT domain)
+template <typename T>
+__global__ void __launch_bounds__(256) rns_key_mac_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, int comps, uint32_t levels,
+                                                          const T *__restrict__ digits, const T *__restrict__ key, T *__restrict__ out,
+                                                          size_t n, size_t batch) {
+    using W = typename WideOf<T>::type;
+    const size_t per_ct = (size_t)comps * limbs * n, total = batch * per_ct;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t ct = gid / per_ct, rem = gid % per_ct;
+        const int c = (int)(rem / ((size_t)limbs * n));
+        const int limb = (int)((rem / n) % limbs);
+        const size_t i = rem % n;
+        const Barrett<T> br = lc.br[limb];
+        W acc = 0;
+        uint32_t terms = 0;
+        for (int r = 0; r < comps; r++) {
+            for (uint32_t l = 0; l < levels; l++) {
+                const T d = digits[(((ct * comps + r) * levels + l) * limbs + limb) * n + i];
+                const T k = key[((((size_t)r * levels + l) * comps + c) * limbs + limb) * n + i];
+                if (terms == 16) {  // reduce_dot_product chunking (compact/mod.rs:14)
+                    acc = barrett_reduce_wide(br, (T)acc, (T)(acc >> (sizeof(T) * 8)));
+                    terms = 1;
+                }
+                acc += (W)d * k;
+                terms++;
+            }
+        }
+        out[gid] = barrett_reduce_wide(br, (T)acc, (T)(acc >> (sizeof(T) * 8)));
+    }
+}
+
+// fused centred lift * scale + accumulate (base.rs:326-386)
+template <typename T> struct LiftScaleConsts {
+    T q[kMaxLimbs], temp[kMaxLimbs], f[kMaxLimbs], fq[kMaxLimbs];
+    T half;
+    int limbs, unsigned_mode;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) rns_lift_scaled_acc_kernel(const __grid_constant__ LiftScaleConsts<T> lc, const T *__restrict__ small,
+                                                                  T *__restrict__ acc, size_t count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const T v = small[i];
+        for (int l = 0; l < lc.limbs; l++) {
+            const T centred = (lc.unsigned_mode || v < lc.half) ? v : lc.temp[l] + v;
+            const size_t o = (size_t)l * count + i;
+            acc[o] = mod_add<T>(acc[o], shoup<T>(centred, lc.f[l], lc.fq[l], lc.q[l]), lc.q[l]);
+        }
+    }
+}
+
+// p * X^r in Z_q[X]/(X^N+1), r in [0, 2N): rotate right by r mod N, negate the wrapped part, flip all when r >= N.
+// polys are [batch][limbs][N]; degrees[batch]
+template <typename T>
+__global__ void __launch_bounds__(256) mul_monomial_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, const uint32_t *__restrict__ degrees,
+                                                           const T *__restrict__ in, T *__restrict__ out, uint32_t log_n, size_t batch) {
+    const uint32_t n = 1u << log_n, mask2 = 2 * n - 1;
+    const size_t total = batch * (size_t)limbs * n;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = gid >> log_n, b = poly / limbs;
+        const int limb = (int)(poly % limbs);
+        const uint32_t i = (uint32_t)(gid & (n - 1));
+        const uint32_t r = degrees[b] & mask2;
+        const uint32_t srcw = (i - r) & mask2;  // out[i] = sign * in[(i - r) mod 2N]
+        const T v = in[(poly << log_n) + (srcw & (n - 1))];
+        out[gid] = srcw >= n ? mod_neg<T>(v, lc.br[limb].q) : v;
+    }
+}
+
+// out[row] = sum_i a[row][i] * b[row][i] mod q ; one CTA per row
+template <typename T>
+__global__ void __launch_bounds__(256) dot_product_kernel(const Barrett<T> br, const T *__restrict__ a, const T *__restrict__ b,
+                                                          T *__restrict__ out, size_t n) {
+    using W = typename WideOf<T>::type;
+    __shared__ T partial[256];
+    const size_t row = blockIdx.x;
+    const T *pa = a + row * n, *pb = b + row * n;
+    T acc = 0;
+    W wide = 0;
+    uint32_t terms = 0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        wide += (W)pa[i] * pb[i];
+        if (++terms == 16) {
+            acc = mod_add<T>(acc, barrett_reduce_wide(br, (T)wide, (T)(wide >> (sizeof(T) * 8))), br.q);
+            wide = 0;
+            terms = 0;
+        }
+    }
+    acc = mod_add<T>(acc, barrett_reduce_wide(br, (T)wide, (T)(wide >> (sizeof(T) * 8))), br.q);
+    partial[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) partial[threadIdx.x] = mod_add<T>(partial[threadIdx.x], partial[threadIdx.x + s], br.q);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[row] = partial[0];
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+template <typename T> static void hbig_mul_word(std::vector<T> &a, T v) {
+    using W = typename host::Wide<T>::type;
+    T carry = 0;
+    for (auto &w : a) {
+        const W s = (W)w * v + carry;
+        w = (T)s;
+        carry = (T)(s >> host::Wide<T>::BITS);
+    }
+    if (carry) a.push_back(carry);
+}
+template <typename T> static T hbig_mod_word(const std::vector<T> &a, T q) {
+    using W = typename host::Wide<T>::type;
+    W r = 0;
+    for (size_t i = a.size(); i-- > 0;) r = ((r << host::Wide<T>::BITS) | a[i]) % q;
+    return (T)r;
+}
+template <typename T> static int hbig_bits(const std::vector<T> &a) {
+    for (size_t i = a.size(); i-- > 0;)
+        if (a[i]) return (int)(i * host::Wide<T>::BITS) + host::bit_length<T>(a[i]);
+    return 0;
+}
+template <typename T> static void hbig_shl(std::vector<T> &a, unsigned s) {
+    constexpr int B = host::Wide<T>::BITS;
+    const size_t len = a.size();
+    while (s >= (unsigned)B) {
+        for (size_t i = len; i-- > 1;) a[i] = a[i - 1];
+        a[0] = 0;
+        s -= B;
+    }
+    if (!s) return;
+    for (size_t i = len; i-- > 0;) a[i] = (T)((a[i] << s) | (i ? (a[i - 1] >> (B - s)) : 0));
+}
+template <typename T> static bool hbig_lt(const std::vector<T> &a, const std::vector<T> &b) {
+    for (size_t i = a.size(); i-- > 0;)
+        if (a[i] != b[i]) return a[i] < b[i];
+    return false;
+}
+template <typename T> static T hgcd(T a, T b) {
+    while (b) {
+        const T t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+template <typename T> static T hmodinv(T a, T m) {
+    using W = typename host::Wide<T>::type;
+    using S = typename std::conditional<sizeof(T) == 8, __int128, int64_t>::type;
+    S t = 0, nt = 1;
+    W r = m, nr = a % m;
+    while (nr) {
+        const W qd = r / nr;
+        const S tt = t - (S)qd * nt;
+        t = nt;
+        nt = tt;
+        const W tr = r - qd * nr;
+        r = nr;
+        nr = tr;
+    }
+    if (r != 1) return 0;
+    if (t < 0) t += (S)m;
+    return (T)t;
+}
+
+// RNSBase::new + BigUintApproxSignedBasis::new (base.rs:79-122, big_integer/basis.rs:40-211)
+template <typename T> int make_rns(const T *moduli, size_t limbs, uint32_t log_basis, uint32_t levels_in, RnsDev<T> &r) {
+    constexpr int B = host::Wide<T>::BITS;
+    memset(&r, 0, sizeof(r));
+    if (limbs == 0) return 6;                                   // RNSError::EmptyBase
+    if (limbs > (size_t)kRnsMaxLimbs) return 9;
+    for (size_t i = 0; i < limbs; i++) {
+        if (moduli[i] < 2) return 9;
+        for (size_t j = i + 1; j < limbs; j++)
+            if (hgcd<T>(moduli[i], moduli[j]) != 1) return 7;   // RNSError::CoPrimeError
+    }
+    std::vector<T> prod{1};
+    for (size_t i = 0; i < limbs; i++) hbig_mul_word<T>(prod, moduli[i]);
+    const int bits = hbig_bits<T>(prod);
+    const int value_len = (bits + B - 1) / B;
+    if (value_len > kRnsMaxWords) return 9;
+    prod.resize(value_len, 0);
+    r.limbs = (int)limbs;
+    r.value_len = value_len;
+    for (int k = 0; k < value_len; k++) r.product[k] = prod[k];
+    for (size_t i = 0; i < limbs; i++) {
+        r.q[i] = moduli[i];
+        std::vector<T> p{1};
+        for (size_t j = 0; j < limbs; j++)
+            if (j != i) hbig_mul_word<T>(p, moduli[j]);
+        p.resize(value_len, 0);
+        for (int k = 0; k < value_len; k++) r.punct[i][k] = p[k];
+        const T inv = hmodinv<T>(hbig_mod_word<T>(p, moduli[i]), moduli[i]);
+        if (inv == 0 && moduli[i] != 1) return 7;
+        r.inv_punct[i] = inv;
+        r.inv_punct_q[i] = host::shoup_quot<T>(inv, moduli[i]);
+    }
+    if (log_basis == 0) return 0;  // RNS base only (compose / decompose)
+    if ((int)log_basis >= B) return 9;
+    uint32_t levels = (uint32_t)bits / log_basis, drop = (uint32_t)bits - levels * log_basis;
+    if (levels_in) {
+        if (levels < levels_in) return 9;
+        levels = levels_in;
+        drop = (uint32_t)bits - levels * log_basis;
+    }
+    if (levels == 0) return 9;
+    r.log_basis = log_basis;
+    r.levels = levels;
+    r.drop_bits = drop;
+    r.basis_m1 = (T)(((T)1 << log_basis) - 1);
+    r.carry_mask = log_basis == 1 ? (T)2 : (T)(((T)1 << log_basis) | ((T)1 << (log_basis - 1)));
+    r.has_init_mask = drop > 0;
+    if (drop > 0) {
+        r.init_index = (int)((drop - 1) / B);
+        r.init_mask = (T)1 << ((drop - 1) % B);
+    }
+    std::vector<T> value(value_len, 0);
+    bool have = false;
+    if (log_basis == 1) {
+        if (drop != 0) {
+            for (uint32_t i = 0; i < levels; i++) {
+                hbig_shl<T>(value, 1);
+                value[0] |= 1;
+            }
+            hbig_shl<T>(value, 1);
+            value[0] |= 1;
+            hbig_shl<T>(value, drop - 1);
+            have = hbig_lt<T>(value, prod);
+        }
+    } else {
+        for (uint32_t i = 0; i < levels; i++) {
+            hbig_shl<T>(value, log_basis);
+            value[0] |= (T)(r.basis_m1 >> 1);
+        }
+        if (drop > 0) {
+            hbig_shl<T>(value, 1);
+            value[0] |= 1;
+            hbig_shl<T>(value, drop - 1);
+        } else {
+            T one = 1;
+            for (int i = 0; i < value_len && one; i++) {
+                value[i] = (T)(value[i] + one);
+                one = value[i] == 0;
+            }
+        }
+        have = hbig_lt<T>(value, prod);
+    }
+    r.has_threshold = have;
+    for (int k = 0; k < value_len; k++) r.threshold[k] = value[k];
+    // add = (2^bits - 1) - (Q - 1)
+    std::vector<T> add(value_len, (T)~(T)0);
+    const int unused = value_len * B - bits;
+    if (unused) add[value_len - 1] = (T)(add[value_len - 1] >> unused);
+    std::vector<T> qm1(prod);
+    {
+        T one = 1;
+        for (int i = 0; i < value_len && one; i++) {
+            const T o = qm1[i];
+            qm1[i] = (T)(o - one);
+            one = o == 0;
+        }
+    }
+    T borrow = 0;
+    for (int i = 0; i < value_len; i++) {
+        const T ai = add[i], bi = qm1[i];
+        add[i] = (T)(ai - bi - borrow);
+        borrow = (ai < bi) || (ai == bi && borrow) ? 1 : 0;
+    }
+    for (int k = 0; k < value_len; k++) r.add[k] = add[k];
+    return 0;
+}
+template int make_rns<uint32_t>(const uint32_t *, size_t, uint32_t, uint32_t, RnsDev<uint32_t> &);
+template int make_rns<uint64_t>(const uint64_t *, size_t, uint32_t, uint32_t, RnsDev<uint64_t> &);
+
+template <typename T> cudaError_t launch_rns_compose(const RnsDev<T> &r, const T *residues, T *big, size_t count, cudaStream_t s) {
+    if (!count) return cudaSuccess;
+    rns_compose_kernel<T><<<grid_for(count, 128), 128, 0, s>>>(r, residues, big, count);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T> cudaError_t launch_rns_decompose(const RnsDev<T> &r, const T *big, T *residues, size_t count, cudaStream_t s) {
+    if (!count) return cudaSuccess;
+    rns_decompose_kernel<T><<<grid_for(count, 128), 128, 0, s>>>(r, big, residues, count);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_rns_gadget(const RnsDev<T> &r, const T *residues, T *digits, size_t count, size_t polys, size_t in_stride, size_t out_stride,
+                              cudaStream_t s) {
+    if (!count || !polys) return cudaSuccess;
+    rns_gadget_kernel<T><<<grid_for(count * polys, 128), 128, 0, s>>>(r, residues, digits, count, polys, in_stride, out_stride);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_rns_key_mac(const LimbConsts<T> &lc, int limbs, int comps, uint32_t levels, const T *digits, const T *key, T *out, size_t n,
+                               size_t batch, cudaStream_t s) {
+    if (!batch) return cudaSuccess;
+    rns_key_mac_kernel<T><<<grid_for(batch * comps * limbs * n, 256), 256, 0, s>>>(lc, limbs, comps, levels, digits, key, out, n, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_rns_lift_scaled_acc(const T *moduli, int limbs, T small_modulus, const T *scalars, const T *small, T *acc, size_t count,
+                                       cudaStream_t s) {
+    if (!count) return cudaSuccess;
+    LiftScaleConsts<T> lc;
+    lc.limbs = limbs;
+    lc.unsigned_mode = small_modulus == 2;
+    lc.half = (T)((small_modulus + 1) / 2);
+    for (int l = 0; l < limbs; l++) {
+        lc.q[l] = moduli[l];
+        lc.temp[l] = moduli[l] - small_modulus;
+        lc.f[l] = scalars[l];
+        lc.fq[l] = host::shoup_quot<T>(scalars[l], moduli[l]);
+    }
+    rns_lift_scaled_acc_kernel<T><<<grid_for(count, 256), 256, 0, s>>>(lc, small, acc, count);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_mul_monomial(const LimbConsts<T> &lc, int limbs, const uint32_t *degrees, const T *in, T *out, uint32_t log_n, size_t batch,
+                                cudaStream_t s) {
+    if (!batch) return cudaSuccess;
+    mul_monomial_kernel<T><<<grid_for((batch * limbs) << log_n, 256), 256, 0, s>>>(lc, limbs, degrees, in, out, log_n, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T> cudaError_t launch_dot_product(const Barrett<T> &br, const T *a, const T *b, T *out, size_t rows, size_t n, cudaStream_t s) {
+    if (!rows) return cudaSuccess;
+    dot_product_kernel<T><<<(unsigned)rows, 256, 0, s>>>(br, a, b, out, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+#define PFHE_INST(T)                                                                                                                         \
+    template cudaError_t launch_rns_compose<T>(const RnsDev<T> &, const T *, T *, size_t, cudaStream_t);                                     \
+    template cudaError_t launch_rns_decompose<T>(const RnsDev<T> &, const T *, T *, size_t, cudaStream_t);                                   \
+    template cudaError_t launch_rns_gadget<T>(const RnsDev<T> &, const T *, T *, size_t, size_t, size_t, size_t, cudaStream_t);              \
+    template cudaError_t launch_rns_key_mac<T>(const LimbConsts<T> &, int, int, uint32_t, const T *, const T *, T *, size_t, size_t,        \
+                                               cudaStream_t);                                                                                \
+    template cudaError_t launch_rns_lift_scaled_acc<T>(const T *, int, T, const T *, const T *, T *, size_t, cudaStream_t);                  \
+    template cudaError_t launch_mul_monomial<T>(const LimbConsts<T> &, int, const uint32_t *, const T *, T *, uint32_t, size_t, cudaStream_t); \
+    template cudaError_t launch_dot_product<T>(const Barrett<T> &, const T *, const T *, T *, size_t, size_t, cudaStream_t);
+PFHE_INST(uint32_t)
+PFHE_INST(uint64_t)
+
+}  // namespace pfhe

@@ -1,0 +1,97 @@
+"""Exactness budget of the lazy FP64-pipe butterflies (primus_fhe_b200/csrc/ntt_core.cuh, struct F64LazyField).
+
+Every value is an integer held in a double.  One modular product mulmod_c(y, w), 0 <= w < q:
+    h = RN(y*w); l = fma(y, w, -h)            (exact split P = h + l)
+    t = fma(h, qinv, M_c), M_c = 1.5*2^(52+c) (one rounding to a multiple of 2^c, valid while |h*qinv| < 2^(51+c))
+    k = t - M_c;  r = fma(-k, q, h) + l       (exact while the intermediate integers stay below 2^53)
+    |k - P/q| <= 2^(c-1) + |P/q| * (2^-53 + 2^-53 + 2^-106)   =>   |r| <= q * (2^(c-1) + |y| * 2^-52 * (1 + 2^-53))
+fold(x):  k = rint(x*qinv) by the same trick (c = 0), x - k q:  |result| <= q/2 + |x| * 2^-52 * ... < q/2 + 1.
+This script walks the stage schedules used by the kernels with exact rationals for the worst admissible modulus
+and asserts every precondition (k range, integer exactness of sums).  Run: python tools/f64_bounds.py
+"""
+from fractions import Fraction as Fr
+
+QMAX = (1 << 50) - 1024          # use_f64 requires q <= 2^50 - 2^10 (capi.cu)
+EPS = Fr(1, 1 << 52) * (1 + Fr(1, 1 << 53))
+LIMIT = Fr(1 << 53)              # integers up to 2^53 are exact in a double
+
+FWD_LEVEL = [0, 0, 0, 1, 2]      # magic level by stage-since-fold (forward, CT)
+INV_LEVEL = [0, 1, 2, 3]         # inverse (GS): the sum path doubles every stage, so the level follows it
+
+
+def mul_bound(b, c, q):
+    # precondition of the magic-constant rounding
+    assert b * (1 + Fr(1, 1 << 52)) < Fr(1 << (51 + c)), ("k range", float(b / q), c)
+    t = q * (Fr(1 << c, 2) + b * EPS)
+    # h - k q = r - l must be an exact integer double: |r| + |l| < 2^53, |l| <= ulp(P)/2 <= |P| 2^-53
+    assert t + b * q * Fr(1, 1 << 53) < LIMIT
+    return t
+
+
+def fold_bound(b, q):
+    assert b <= LIMIT
+    return q / 2 + b * EPS + 1
+
+
+def forward(stages_per_pass, q):
+    b = (q + 1) / 2              # centred load (exact 64-bit compare): [0,q) -> [-(q-1)/2, (q+1)/2)
+    worst = b
+    for p, ns in enumerate(stages_per_pass):
+        if p:
+            b = fold_bound(b, q)
+        for s in range(ns):
+            t = mul_bound(b, FWD_LEVEL[s], q)
+            b = b + t
+            assert b <= LIMIT, ("fwd sum", p, s, float(b / q))
+            worst = max(worst, b)
+    out = fold_bound(b, q)       # canonical output: fold, + q bias, one conditional subtract
+    assert out < q
+    return float(worst / q)
+
+
+def inverse(stages_per_pass, q):
+    # stages_per_pass in execution order (last pass first); the final stage multiplies both outputs (n^-1 fused)
+    b = (q + 1) / 2
+    worst = b
+    total = sum(stages_per_pass)
+    done = 0
+    for p, ns in enumerate(stages_per_pass):
+        if p:
+            b = fold_bound(b, q)
+        since = 0
+        for s in range(ns):
+            if since == len(INV_LEVEL):
+                b = fold_bound(b, q)
+                since = 0
+            sd = 2 * b           # s = x + y, d = x - y
+            assert sd <= LIMIT, ("inv sum", p, s, float(sd / q))
+            t = mul_bound(sd, INV_LEVEL[since], q)
+            done += 1
+            b = t if done == total else max(sd, t)
+            worst = max(worst, sd)
+            since += 1
+    out = fold_bound(b, q)
+    assert out < q
+    return float(worst / q)
+
+
+def plan(logn, loge):
+    npass = (logn + loge - 1) // loge
+    first = logn - (npass - 1) * loge
+    return [first] + [loge] * (npass - 1)
+
+
+def check_all():
+    res = {}
+    for q in (QMAX, (1 << 49) + 1, 1125899906826241):
+        for logn in range(10, 15):
+            for loge in (3, 4, 5):
+                pl = plan(logn, loge)
+                res[(q, logn, loge)] = (forward(pl, Fr(q)), inverse(list(reversed(pl)), Fr(q)))
+    return res
+
+
+if __name__ == "__main__":
+    for k, v in sorted(check_all().items()):
+        print(k, "max |value|/q  fwd %.3f  inv %.3f" % v)
+    print("all exactness preconditions hold for q <=", QMAX)
