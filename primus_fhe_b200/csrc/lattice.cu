@@ -130,6 +130,7 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = F::load(gadget_level<T>(g, adj[j], shift, carry[j]), cx);
+                sync();  // the exchange buffer was last read with the previous transform's final pattern
                 Core::template fwd_from<0>(x, sm, tb, cx, t, sync);
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);

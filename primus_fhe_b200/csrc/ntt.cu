@@ -20,10 +20,6 @@ namespace pfhe {
 std::atomic<uint64_t> g_launches{0};
 
 int choose_loge(int bits, int log_n) {
-    if (bits == 64 && log_n == 12) {  // experiment hook (tuning only): PFHE_LOGE12=3|4|5
-        const char *e = getenv("PFHE_LOGE12");
-        if (e && e[0] >= '3' && e[0] <= '5') return e[0] - '0';
-    }
     if (bits == 64) {
         switch (log_n) {
             case 10: return 5;
@@ -43,6 +39,21 @@ int choose_loge(int bits, int log_n) {
         case 15: return 5;
         default: return 0;
     }
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 struct SyncBlock {
@@ -139,6 +150,7 @@ polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     typename SyncFor<TPP>::type sync;
     Elem xa[E], xb[E];
     Core::forward_g2r(a + poly * N, xa, sm, tb, c, t, sync);
+    sync();  // the exchange buffer is reused with the first pass's pattern
     Core::forward_g2r(b + poly * N, xb, sm, tb, c, t, sync);
     // pointwise product, exact mod q (BarrettModulus::reduce_mul, primus_modulus/src/barrett/ops.rs:276-283)
 #pragma unroll
@@ -314,11 +326,14 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
 }
 
 
-// field selection: u64 tables with q < 2^50 run on the FP64 pipe, everything else on the integer pipe
+// field selection: u64 tables with q < 2^50 run on the FP64 pipe, everything else on the integer pipe.
+// PFHE_F64_LAZY=0 selects the per-stage-fold FP64 butterflies (A/B tuning hook).
 template <typename T, int LOGN, int LOGE, int PPB>
 static cudaError_t run_ntt(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *src, T *dst, size_t npolys, bool fwd,
                            cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
+        static const bool lazy = env_int("PFHE_F64_LAZY", 1) != 0;
+        if (tb0.use_f64 && lazy) return run_ntt_f<F64LazyField, LOGN, LOGE, PPB>(tb0, tables, limbs, src, dst, npolys, fwd, stream);
         if (tb0.use_f64) return run_ntt_f<F64Field, LOGN, LOGE, PPB>(tb0, tables, limbs, src, dst, npolys, fwd, stream);
     }
     return run_ntt_f<IntField<T>, LOGN, LOGE, PPB>(tb0, tables, limbs, src, dst, npolys, fwd, stream);
@@ -327,6 +342,8 @@ template <typename T, int LOGN, int LOGE, int PPB>
 static cudaError_t run_polymul(const DevNtt<T> &tb0, const DevNtt<T> *tables, int limbs, const T *a, const T *b, T *c, size_t npolys,
                                cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
+        static const bool lazy = env_int("PFHE_F64_LAZY", 1) != 0;
+        if (tb0.use_f64 && lazy) return run_polymul_f<F64LazyField, LOGN, LOGE, PPB>(tb0, tables, limbs, a, b, c, npolys, stream);
         if (tb0.use_f64) return run_polymul_f<F64Field, LOGN, LOGE, PPB>(tb0, tables, limbs, a, b, c, npolys, stream);
     }
     return run_polymul_f<IntField<T>, LOGN, LOGE, PPB>(tb0, tables, limbs, a, b, c, npolys, stream);
@@ -359,14 +376,7 @@ cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint6
         switch (tb0.log_n) {
             case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 11: return run_ntt<T, 11, 4, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-            case 12:
-                if (tb0.loge == 3) return run_ntt<T, 12, 3, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-                if (tb0.loge == 5) {
-                    const char *e = getenv("PFHE_PPB12");
-                    if (e && e[0] == '2') return run_ntt<T, 12, 5, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-                    return run_ntt<T, 12, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-                }
-                return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 12: return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 13: return run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 14: return run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
         }

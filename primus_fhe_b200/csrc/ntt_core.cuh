@@ -42,6 +42,61 @@ template <typename T> struct DevNtt {
 
 template <typename T> __device__ __forceinline__ typename Word<T>::Pair ld_pair(const typename Word<T>::Pair *p) { return __ldg(p); }
 
+
+// Streaming global accesses: polynomial data is touched exactly once per kernel, so it must not evict the twiddle
+// tables from L1 (they are re-read by every polynomial): loads bypass L1 allocation, stores are marked streaming.
+#ifndef PFHE_STREAM_HINTS
+#define PFHE_STREAM_HINTS 1
+#endif
+__device__ __forceinline__ uint32_t ldg_stream(const uint32_t *p) {
+#if PFHE_STREAM_HINTS
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint64_t ldg_stream(const uint64_t *p) {
+#if PFHE_STREAM_HINTS
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+#if PFHE_STREAM_HINTS
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void stg_stream(uint32_t *p, uint32_t v) {
+#if PFHE_STREAM_HINTS
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(uint64_t *p, uint64_t v) {
+#if PFHE_STREAM_HINTS
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(uint4 *p, uint4 v) {
+#if PFHE_STREAM_HINTS
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+    *p = v;
+#endif
+}
+
 // Compile-time pass plan shared by host (table layout) and device.
 template <int LOGN, int LOGE> struct Plan {
     static_assert(LOGE >= 1 && LOGN >= LOGE, "bad plan");
@@ -105,12 +160,16 @@ template <typename T> struct IntField {
     __device__ __forceinline__ static const Tw *fwd_tw(const DevNtt<T> &tb) { return tb.fwd_pass; }
     __device__ __forceinline__ static const Tw *inv_tw(const DevNtt<T> &tb) { return tb.inv_pass; }
     __device__ __forceinline__ static Tw ld(const Tw *p) { return __ldg(p); }
+    // lazy-fold interface (see F64LazyField): the integer butterflies renormalise every stage, nothing to do
+    static constexpr bool kLazy = false;
+    static constexpr int kFwdMax = 64, kInvMax = 64;
+    __device__ __forceinline__ static void refold(Elem &, const Ctx &) {}
     __device__ __forceinline__ static Elem load(T w, const Ctx &) { return w; }          // fwd: < 4q, inv: < 2q
     __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &) { return raw; }
-    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c) { fwd_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
-    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c) { inv_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) { fwd_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
+    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) { inv_bfly<T>(x, y, w.x, w.y, c.q, c.two_q); }
     // final inverse stage fused with n^-1 (transform.rs:283-318); outputs canonical
-    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) {
         const T tx = x + y, ty = x + c.two_q - y;
         x = shoup<T>(tx, c.inv_n, c.inv_n_q, c.q);
         y = shoup<T>(ty, w.x, w.y, c.q);
@@ -179,20 +238,23 @@ struct F64Field {
     // inputs are canonical words in [0, q) (lazy-range callers are canonicalised by a pointwise pre-pass, capi.cu)
     __device__ __forceinline__ static Elem load(uint64_t w, const Ctx &) { return from_u64(w); }
     __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &c) { return load((uint64_t)__double_as_longlong(raw), c); }
+    static constexpr bool kLazy = false;
+    static constexpr int kFwdMax = 64, kInvMax = 64;
+    __device__ __forceinline__ static void refold(Elem &, const Ctx &) {}
     // |x|,|y| < 2q on entry and exit
-    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) {
         const double xt = fold(x, c);
         const double t = mulmod(y, w, c);
         x = __dadd_rn(xt, t);
         y = __dsub_rn(xt, t);
     }
     // |x|,|y| < q on entry and exit
-    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) {
         const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
         x = fold(s, c);
         y = mulmod(d, w, c);
     }
-    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c) {
+    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) {
         const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
         x = mulmod(s, c.inv_n, c);
         y = mulmod(d, w, c);
@@ -214,6 +276,83 @@ struct F64Field {
     // key-MAC results (doubles in (-q, q)) as inverse-transform inputs / as canonical output bits
     __device__ __forceinline__ static Elem from_mac(double v, const Ctx &) { return v; }
     __device__ __forceinline__ static Elem mac_bits(double v, const Ctx &c) { return __longlong_as_double((long long)inv_word(v, c)); }
+};
+
+
+// FP64 pipe, lazy folds.  Same exact-integer-in-a-double arithmetic as F64Field, but the per-stage conditional fold of
+// the sum path (1 DADD + 5 integer-ALU instructions per butterfly) is gone: q < 2^50 leaves three spare mantissa bits,
+// so values are allowed to grow for a whole register pass and every element is folded ONCE per pass with
+// x - q*rint(x/q) (3 FP64 instructions, no ALU).  A butterfly is then 6 (product) + 2 (add/sub) FP64 instructions.
+// The product rounds its quotient to a multiple of 2^c with the magic constant 1.5*2^(52+c); the level c grows with the
+// number of stages since the last fold so that the quotient always fits (tools/f64_bounds.py walks every schedule used
+// here with exact rationals and asserts the k range and the integer exactness of every sum for q <= 2^50 - 2^10):
+//   forward (CT):  level by stage-since-fold {0,0,0,1,2}, |value| < 7.76 q after 5 stages
+//   inverse (GS):  level {0,1,2,3}, the sum path doubles per stage: |value| <= 8 (q/2 + 2) <= 2^53 after 4 stages
+// Loads centre canonical words exactly to [-(q-1)/2, (q+1)/2); stores fold, add q and subtract q conditionally.
+struct F64LazyField : F64Field {
+    struct Ctx {
+        double q, qinv, inv_n;
+        double off1;   // 2^52 + q
+        uint64_t qi, half;  // q, (q+1)/2
+    };
+    static constexpr bool kLazy = true;
+    static constexpr int kFwdMax = 5, kInvMax = 4;
+    __device__ __forceinline__ static Ctx ctx(const DevNtt<uint64_t> &tb) {
+        return Ctx{tb.q_f, tb.qinv_f, tb.inv_n_f, kTwo52 + tb.q_f, tb.q, (tb.q + 1) >> 1};
+    }
+    __device__ __forceinline__ static double magic(int level) {
+        return level <= 0 ? 6755399441055744.0 : level == 1 ? 13510798882111488.0 : level == 2 ? 27021597764222976.0 : 54043195528445952.0;
+    }
+    __device__ __forceinline__ static double mulmod(double y, double w, const Ctx &c, int level) {
+        const double m = magic(level);
+        const double h = __dmul_rn(y, w);
+        const double l = __fma_rn(y, w, -h);
+        const double t = __fma_rn(h, c.qinv, m);
+        const double k = __dsub_rn(t, m);
+        const double d = __fma_rn(-k, c.q, h);
+        return __dadd_rn(d, l);
+    }
+    // any |x| <= 2^53 -> |x| <= q/2 + 1
+    __device__ __forceinline__ static void refold(double &x, const Ctx &c) {
+        const double t = __fma_rn(x, c.qinv, kMagic);
+        const double k = __dsub_rn(t, kMagic);
+        x = __fma_rn(-k, c.q, x);
+    }
+    __device__ __forceinline__ static int fwd_level(int since) { return since < 3 ? 0 : since - 2; }
+    __device__ __forceinline__ static Elem load(uint64_t w, const Ctx &c) {
+        const double bias = w >= c.half ? c.off1 : kTwo52;
+        return __dsub_rn(__hiloint2double((int)(0x43300000u | (uint32_t)(w >> 32)), (int)(uint32_t)w), bias);
+    }
+    __device__ __forceinline__ static Elem load_bits(Elem raw, const Ctx &c) { return load((uint64_t)__double_as_longlong(raw), c); }
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c, int since) {
+        const double t = mulmod(y, w, c, fwd_level(since));
+        y = __dsub_rn(x, t);
+        x = __dadd_rn(x, t);
+    }
+    __device__ __forceinline__ static void inv(Elem &x, Elem &y, const Tw &w, const Ctx &c, int since) {
+        const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
+        x = s;
+        y = mulmod(d, w, c, since);
+    }
+    __device__ __forceinline__ static void inv_last(Elem &x, Elem &y, const Tw &w, const Ctx &c, int since) {
+        const double s = __dadd_rn(x, y), d = __dsub_rn(x, y);
+        x = mulmod(s, c.inv_n, c, since);
+        y = mulmod(d, w, c, since);
+    }
+    __device__ __forceinline__ static uint64_t canon(Elem v, const Ctx &c) {
+        refold(v, c);
+        return csub<uint64_t>(mant(__dadd_rn(v, c.off1)), c.qi);
+    }
+    __device__ __forceinline__ static uint64_t fwd_word(Elem v, const Ctx &c) { return canon(v, c); }
+    __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
+    __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) { return canon(v, c); }
+    // forward outputs (|a|,|b| < 7.76 q) -> centred product, ready for the first inverse pass
+    __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) {
+        refold(b, c);
+        double r = mulmod(a, b, c, 2);
+        refold(r, c);
+        return r;
+    }
 };
 
 template <typename F, int LOGN, int LOGE> struct NttCore {
@@ -248,8 +387,13 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     // ---- register passes -------------------------------------------------------------------
     template <int PASS> __device__ __forceinline__ static void fwd_pass_regs(Elem (&x)[E], const DevNtt<T> &tb, const Ctx &c, int t) {
         constexpr int NS = P::nstages(PASS), FB = P::fb(PASS), NH = P::nh(PASS);
+        static_assert(NS <= F::kFwdMax, "too many forward stages between folds");
         const Tw *tw = F::fwd_tw(tb) + P::pass_offset(PASS);
         const int high = (t >> FB);
+        if (F::kLazy && PASS > 0) {  // pass 0 starts from centred loads
+#pragma unroll
+            for (int j = 0; j < E; j++) F::refold(x[j], c);
+        }
 #pragma unroll
         for (int ls = 0; ls < NS; ls++) {
             const int jb = LOGE - 1 - ls;
@@ -259,7 +403,7 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
 #pragma unroll
                 for (int jl = 0; jl < (1 << jb); jl++) {
                     const int j0 = (jp << (jb + 1)) | jl, j1 = j0 | (1 << jb);
-                    F::fwd(x[j0], x[j1], w, c);
+                    F::fwd(x[j0], x[j1], w, c, ls);
                 }
             }
         }
@@ -270,9 +414,19 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
         constexpr int NS = P::nstages(PASS), FB = P::fb(PASS), NH = P::nh(PASS);
         const Tw *tw = F::inv_tw(tb) + P::pass_offset(PASS);
         const int high = (t >> FB);
+        if (F::kLazy && PASS < P::NPASS - 1) {  // the first inverse pass starts from centred loads / folded products
+#pragma unroll
+            for (int j = 0; j < E; j++) F::refold(x[j], c);
+        }
 #pragma unroll
         for (int ls = NS - 1; ls >= 0; ls--) {
             const int jb = LOGE - 1 - ls;
+            const int done = NS - 1 - ls;  // stages of this pass already executed
+            if (F::kLazy && done > 0 && done % F::kInvMax == 0) {
+#pragma unroll
+                for (int j = 0; j < E; j++) F::refold(x[j], c);
+            }
+            const int since = done % F::kInvMax;
 #pragma unroll
             for (int jp = 0; jp < (1 << ls); jp++) {
                 const Tw w = F::ld(tw + (((1 << ls) - 1 + jp) * NH + high));
@@ -280,9 +434,9 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
                 for (int jl = 0; jl < (1 << jb); jl++) {
                     const int j0 = (jp << (jb + 1)) | jl, j1 = j0 | (1 << jb);
                     if (PASS == 0 && ls == 0)
-                        F::inv_last(x[j0], x[j1], w, c);
+                        F::inv_last(x[j0], x[j1], w, c, since);
                     else
-                        F::inv(x[j0], x[j1], w, c);
+                        F::inv(x[j0], x[j1], w, c, since);
                 }
             }
         }
@@ -323,19 +477,33 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     __device__ __forceinline__ static void copy_g2s(const T *g, Elem *sm, int t) {
 #pragma unroll
         for (int v = t; v < N / CW; v += TPP) {
-            const WVec d = *reinterpret_cast<const WVec *>(g + v * CW);
-            *reinterpret_cast<WVec *>(sm + swz(v * CW)) = d;
+            const uint4 d = ldg_stream(reinterpret_cast<const uint4 *>(g + v * CW));
+            *reinterpret_cast<uint4 *>(sm + swz(v * CW)) = d;
         }
     }
     __device__ __forceinline__ static void copy_s2g(const Elem *sm, T *g, int t) {
 #pragma unroll
         for (int v = t; v < N / CW; v += TPP) {
-            const WVec d = *reinterpret_cast<const WVec *>(sm + swz(v * CW));
-            *reinterpret_cast<WVec *>(g + v * CW) = d;
+            const uint4 d = *reinterpret_cast<const uint4 *>(sm + swz(v * CW));
+            stg_stream(reinterpret_cast<uint4 *>(g + v * CW), d);
         }
     }
 
     // ---- recursive pass drivers ---------------------------------------------------------------
+    // Synchronisation rules of the exchange buffer:
+    //  * the elements a thread loads for pass P are exactly the elements it stores after pass P, so no barrier is
+    //    needed between an sm_load and the following sm_store of the same pass;
+    //  * the exchange between passes P and P+1 (P >= 1) only moves data inside groups of 2^fb(P) consecutive threads
+    //    (the thread-id prefix `high` of pass P is shared by source and destination): when that group is at most a
+    //    warp, __syncwarp replaces the CTA barrier;
+    //  * callers that reuse the buffer with ANOTHER pass's pattern (a second transform, the coalesced copy-out) must
+    //    synchronise the whole thread group themselves.
+    template <int PASS_LO, typename SyncF> __device__ __forceinline__ static void xchg_sync(SyncF sync) {
+        if constexpr (PASS_LO >= 1 && (1 << P::fb(PASS_LO)) <= 32)
+            __syncwarp();
+        else
+            sync();
+    }
     // forward passes PASS..NPASS-1 with x holding pass PASS's elements on entry; on exit x holds the
     // last pass's elements (thread t owns words [t*E, (t+1)*E)), lazy representation.
     template <int PASS, typename SyncF>
@@ -343,9 +511,8 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
         fwd_pass_regs<PASS>(x, tb, c, t);
         if constexpr (PASS + 1 < P::NPASS) {
             sm_store<PASS>(x, sm, t);
-            sync();
+            xchg_sync<PASS>(sync);
             sm_load<PASS + 1>(x, sm, t);
-            sync();  // buffer may be rewritten by the next exchange
             fwd_from<PASS + 1>(x, sm, tb, c, t, sync);
         }
     }
@@ -356,9 +523,8 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
         inv_pass_regs<PASS>(x, tb, c, t);
         if constexpr (PASS > 0) {
             sm_store<PASS>(x, sm, t);
-            sync();
+            xchg_sync<PASS - 1>(sync);
             sm_load<PASS - 1>(x, sm, t);
-            sync();
             inv_from<PASS - 1>(x, sm, tb, c, t, sync);
         }
     }
@@ -369,7 +535,7 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     __device__ __forceinline__ static void forward_g2r(const T *g, Elem (&x)[E], Elem *sm, const DevNtt<T> &tb, const Ctx &c, int t, SyncF sync) {
         constexpr int FB0 = P::fb(0);
 #pragma unroll
-        for (int j = 0; j < E; j++) x[j] = F::load(g[elem_index(FB0, t, j)], c);
+        for (int j = 0; j < E; j++) x[j] = F::load(ldg_stream(g + elem_index(FB0, t, j)), c);
         fwd_from<0>(x, sm, tb, c, t, sync);
     }
     // forward outputs in registers -> canonical words in the swizzled buffer (then copy_s2g)
@@ -384,7 +550,6 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
         copy_g2s(g, sm, t);
         sync();
         sm_load<P::NPASS - 1>(x, sm, t);
-        sync();
 #pragma unroll
         for (int j = 0; j < E; j++) x[j] = F::load_bits(x[j], c);
     }
@@ -392,7 +557,7 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     __device__ __forceinline__ static void inv_regs_to_global(const Elem (&x)[E], T *g, const Ctx &c, int t) {
         constexpr int FB0 = P::fb(0);
 #pragma unroll
-        for (int j = 0; j < E; j++) g[elem_index(FB0, t, j)] = F::inv_word(x[j], c);
+        for (int j = 0; j < E; j++) stg_stream(g + elem_index(FB0, t, j), F::inv_word(x[j], c));
     }
 };
 
