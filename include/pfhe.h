@@ -274,6 +274,82 @@ pfhe_status pfhe_blind_rotate32_batch(const pfhe_ntt32 *t, uint32_t log_basis, u
 pfhe_status pfhe_extract_lwe64_batch(uint64_t q, const uint64_t *rlwe, uint64_t *lwe, size_t n, size_t batch, void *stream);
 pfhe_status pfhe_extract_lwe32_batch(uint32_t q, const uint32_t *rlwe, uint32_t *lwe, size_t n, size_t batch, void *stream);
 
+
+/* ===================================================================================== */
+/* RNS base, multi-word gadget basis and the multi-limb (L > 1) external product           */
+/* ===================================================================================== */
+typedef struct pfhe_rns32 pfhe_rns32; /* RNSBase<u32> primus_rns/src/base.rs:26-122 */
+typedef struct pfhe_rns64 pfhe_rns64; /* RNSBase<u64> */
+
+/* RNSBase::new(moduli) (base.rs:79-122): pairwise-coprime check (RNS_NOT_COPRIME), punctured products Q/q_i and
+ * their inverses.  Up to 8 limbs / 8 words of composed value.  Host-only handle (constants travel as kernel
+ * parameters), usable from any thread and on any device. */
+pfhe_status pfhe_rns64_create(const uint64_t *moduli, size_t count, pfhe_rns64 **out);
+pfhe_status pfhe_rns32_create(const uint32_t *moduli, size_t count, pfhe_rns32 **out);
+void pfhe_rns64_destroy(pfhe_rns64 *r);
+void pfhe_rns32_destroy(pfhe_rns32 *r);
+size_t pfhe_rns64_moduli_count(const pfhe_rns64 *r);
+size_t pfhe_rns32_moduli_count(const pfhe_rns32 *r);
+size_t pfhe_rns64_big_uint_value_len(const pfhe_rns64 *r); /* RNSBase::big_uint_value_len */
+size_t pfhe_rns32_big_uint_value_len(const pfhe_rns32 *r);
+/* moduli_product(): Q as value_len little-endian words into `out` (HOST) */
+pfhe_status pfhe_rns64_moduli_product(const pfhe_rns64 *r, uint64_t *out);
+pfhe_status pfhe_rns32_moduli_product(const pfhe_rns32 *r, uint32_t *out);
+
+/* RNSBase::compose_multiple_values_to (base.rs:638-673): residues [limbs][count] (modulus-major, device) ->
+ * big values [count][value_len] little-endian words (device). */
+pfhe_status pfhe_rns64_compose_batch(const pfhe_rns64 *r, const uint64_t *residues, uint64_t *big, size_t count, void *stream);
+pfhe_status pfhe_rns32_compose_batch(const pfhe_rns32 *r, const uint32_t *residues, uint32_t *big, size_t count, void *stream);
+/* RNSBase::decompose_big_uint_values_to (base.rs:457-481): the inverse map (values need not be < Q). */
+pfhe_status pfhe_rns64_decompose_batch(const pfhe_rns64 *r, const uint64_t *big, uint64_t *residues, size_t count, void *stream);
+pfhe_status pfhe_rns32_decompose_batch(const pfhe_rns32 *r, const uint32_t *big, uint32_t *residues, size_t count, void *stream);
+/* RNSBase::wrapping_decompose_small_values_scaled_add_to (base.rs:326-386, :739-756):
+ * acc[l][i] += scalars[l] * centred_lift(small[i]) mod q_l; acc is [limbs][count] device, scalars HOST. */
+pfhe_status pfhe_rns64_lift_small_scaled_add_batch(const uint64_t *moduli, size_t limbs, uint64_t small_modulus, const uint64_t *scalars,
+                                                   const uint64_t *small, uint64_t *acc, size_t count, void *stream);
+pfhe_status pfhe_rns32_lift_small_scaled_add_batch(const uint32_t *moduli, size_t limbs, uint32_t small_modulus, const uint32_t *scalars,
+                                                   const uint32_t *small, uint32_t *acc, size_t count, void *stream);
+
+/* BigUintApproxSignedBasis::new(Q, log_basis, reverse_length) geometry (primus_decompose/src/big_integer/basis.rs:40-211). */
+pfhe_status pfhe_bigbasis64_geometry(const pfhe_rns64 *r, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits);
+pfhe_status pfhe_bigbasis32_geometry(const pfhe_rns32 *r, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits);
+/* Gadget decomposition of CRT polynomials, fused: compose (base.rs:609-636) -> init_value_carry_slice_inplace
+ * (big_integer/basis.rs:326-367) -> unsigned_decompose_slice_to for every level (big_integer/common.rs:275-325) ->
+ * centred lift to every limb (base.rs:279-315), i.e. the digit pipeline of add_dcrt_glev_mul_crt_poly_assign
+ * (primus_lattice/src/glwe/dcrt.rs:219-236).  residues: [polys][limbs][n] device; digits: [polys][levels][limbs][n]. */
+pfhe_status pfhe_rns64_gadget_decompose_batch(const pfhe_rns64 *r, uint32_t log_basis, uint32_t levels_in, const uint64_t *residues,
+                                              uint64_t *digits, size_t n, size_t polys, void *stream);
+pfhe_status pfhe_rns32_gadget_decompose_batch(const pfhe_rns32 *r, uint32_t log_basis, uint32_t levels_in, const uint32_t *residues,
+                                              uint32_t *digits, size_t n, size_t polys, void *stream);
+
+/* Multi-limb GGSW external product = CrtGlwe::mul_dcrt_ggsw_to (primus_lattice/src/glwe/crt.rs:200-227) [+ into_coeff_form]:
+ * digits (above) -> DCRT forward NTT -> key multiply-accumulate with lazy double-word sums
+ * (glwe/dcrt.rs:108-126; reduce_dot_product, primus_modulus/src/common/compact/slice.rs:371-401) -> optional inverse NTT.
+ * key: device [k+1][levels][k+1][limbs][N] NTT domain; in/out: device [batch][k+1][limbs][N].
+ * `scratch`: device memory for the digits; any size >= ..._scratch_bytes(batch = 1) works, the batch is processed in
+ * chunks that fit (no allocation on the hot path). */
+size_t pfhe_dcrt64_external_product_scratch_bytes(const pfhe_dcrt64 *t, const pfhe_rns64 *r, uint32_t k, uint32_t log_basis,
+                                                  uint32_t levels_in, size_t batch);
+size_t pfhe_dcrt32_external_product_scratch_bytes(const pfhe_dcrt32 *t, const pfhe_rns32 *r, uint32_t k, uint32_t log_basis,
+                                                  uint32_t levels_in, size_t batch);
+pfhe_status pfhe_dcrt64_external_product_batch(const pfhe_dcrt64 *t, const pfhe_rns64 *r, uint32_t k, uint32_t log_basis,
+                                               uint32_t levels_in, const uint64_t *key, const uint64_t *in, uint64_t *out, size_t batch,
+                                               int to_coeff, void *scratch, size_t scratch_bytes, void *stream);
+pfhe_status pfhe_dcrt32_external_product_batch(const pfhe_dcrt32 *t, const pfhe_rns32 *r, uint32_t k, uint32_t log_basis,
+                                               uint32_t levels_in, const uint32_t *key, const uint32_t *in, uint32_t *out, size_t batch,
+                                               int to_coeff, void *scratch, size_t scratch_bytes, void *stream);
+
+/* Polynomial::mul_monomial_assign / CrtGlwe::mul_monic_monomial_assign (primus_poly/src/poly/mul.rs:74-99,
+ * primus_lattice/src/glwe/crt.rs:76-114): out = in * X^degree in Z_q[X]/(X^N+1) per limb; in/out [batch][limbs][N]
+ * device (out != in), degrees[batch] device, each taken mod 2N. */
+pfhe_status pfhe_poly64_mul_monomial_batch(const uint64_t *moduli, size_t limbs, const uint32_t *degrees, const uint64_t *in,
+                                           uint64_t *out, uint32_t log_n, size_t batch, void *stream);
+pfhe_status pfhe_poly32_mul_monomial_batch(const uint32_t *moduli, size_t limbs, const uint32_t *degrees, const uint32_t *in,
+                                           uint32_t *out, uint32_t log_n, size_t batch, void *stream);
+/* reduce_dot_product (primus_modulus/src/common/compact/slice.rs:371-438): out[row] = sum_i a[row][i]*b[row][i] mod q. */
+pfhe_status pfhe_mod64_dot_product_batch(uint64_t q, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t rows, size_t n, void *stream);
+pfhe_status pfhe_mod32_dot_product_batch(uint32_t q, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t rows, size_t n, void *stream);
+
 /* ===================================================================================== */
 /* Plumbing for hosts without a CUDA binding of their own (the Rust FFI crate, tests)      */
 /* ===================================================================================== */

@@ -382,22 +382,137 @@ class ApproxSignedBasis:
 
 
 class RNSBase:
-    """The limb-handling part of RNSBase that is on the hot path (primus_rns/src/base.rs:279-315)."""
+    """RNSBase (primus_rns/src/base.rs:26-122): constructor checks (EmptyBase / CoPrimeError), compose / decompose
+    between residues [L][count] and little-endian big values [count][value_len], centred lifts of small values."""
 
     def __init__(self, moduli, bits=64):
-        if len(moduli) == 0:
-            raise PfheError(6)
         self.moduli, self.bits = [int(m) for m in moduli], bits
+        self._h = C.c_void_p()
+        self._p = f"pfhe_rns{bits}_"
+        L = len(self.moduli)
+        arr = (_ct(bits) * max(1, L))(*self.moduli)
+        f = getattr(lib(), self._p + "create"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(arr, L, C.byref(self._h)))
+        g = getattr(lib(), self._p + "big_uint_value_len"); g.argtypes = [C.c_void_p]; g.restype = C.c_size_t
+        self.value_len = int(g(self._h))
+
+    @classmethod
+    def new(cls, moduli, bits=64):
+        return cls(moduli, bits)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
 
     def moduli_count(self): return len(self.moduli)
+    def big_uint_value_len(self): return self.value_len
+
+    def moduli_product(self) -> int:
+        out = (_ct(self.bits) * self.value_len)()
+        f = getattr(lib(), self._p + "moduli_product"); f.argtypes = [C.c_void_p, C.c_void_p]
+        check(f(self._h, out))
+        return sum(int(w) << (self.bits * i) for i, w in enumerate(out))
+
+    def _marr(self):
+        return (_ct(self.bits) * len(self.moduli))(*self.moduli)
+
+    def compose_multiple_values_to(self, multi_residues, big_values):
+        """multi_residues: CUDA [L][count]; big_values: CUDA [count][value_len]."""
+        count = multi_residues.numel() // len(self.moduli)
+        f = getattr(lib(), self._p + "compose_batch"); f.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(multi_residues, self.bits), _dev_ptr(big_values, self.bits, count * self.value_len), count, _stream()))
+
+    def decompose_big_uint_values_to(self, big_values, multi_residues):
+        count = big_values.numel() // self.value_len
+        f = getattr(lib(), self._p + "decompose_batch"); f.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(big_values, self.bits), _dev_ptr(multi_residues, self.bits, count * len(self.moduli)), count, _stream()))
 
     def wrapping_decompose_small_values_to(self, small, multi_residues, small_modulus):
         L = len(self.moduli)
-        m = (_ct(self.bits) * L)(*self.moduli)
         f = getattr(lib(), f"pfhe_rns{self.bits}_lift_small_batch")
         f.argtypes = [C.c_void_p, C.c_size_t, _ct(self.bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
-        check(f(m, L, int(small_modulus), _dev_ptr(small, self.bits), _dev_ptr(multi_residues, self.bits, small.numel() * L),
+        check(f(self._marr(), L, int(small_modulus), _dev_ptr(small, self.bits), _dev_ptr(multi_residues, self.bits, small.numel() * L),
                 small.numel(), _stream()))
+
+    def wrapping_decompose_small_values_scaled_add_to(self, small, acc, small_modulus, scalars):
+        """acc[l] += scalars[l] * centred_lift(small) mod q_l (base.rs:326-386)."""
+        L = len(self.moduli)
+        sc = (_ct(self.bits) * L)(*[int(x) for x in scalars])
+        f = getattr(lib(), f"pfhe_rns{self.bits}_lift_small_scaled_add_batch")
+        f.argtypes = [C.c_void_p, C.c_size_t, _ct(self.bits), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(self._marr(), L, int(small_modulus), sc, _dev_ptr(small, self.bits), _dev_ptr(acc, self.bits, small.numel() * L),
+                small.numel(), _stream()))
+
+
+class BigUintApproxSignedBasis:
+    """BigUintApproxSignedBasis::new(Q, log_basis, reverse_length) over an RNS base
+    (primus_decompose/src/big_integer/basis.rs:17-211) + the fused digit pipeline of the gadget product."""
+
+    def __init__(self, rns: RNSBase, log_basis, reverse_length=None):
+        self.rns, self.bits, self._log_basis, self._rev = rns, rns.bits, log_basis, reverse_length or 0
+        lv, dr = C.c_uint32(0), C.c_uint32(0)
+        f = getattr(lib(), f"pfhe_bigbasis{self.bits}_geometry")
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        check(f(rns._h, log_basis, self._rev, C.byref(lv), C.byref(dr)))
+        self._levels, self._drop = lv.value, dr.value
+
+    def decompose_length(self): return self._levels
+    def drop_bits(self): return self._drop
+    def log_basis(self): return self._log_basis
+    def basis_value(self): return 1 << self._log_basis
+
+    def gadget_decompose_batch(self, residues, digits, n):
+        """residues: CUDA [polys][L][n] (CRT polynomials); digits: CUDA [polys][levels][L][n] lifted digits."""
+        L = self.rns.moduli_count()
+        polys = residues.numel() // (L * n)
+        f = getattr(lib(), f"pfhe_rns{self.bits}_gadget_decompose_batch")
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        check(f(self.rns._h, self._log_basis, self._rev, _dev_ptr(residues, self.bits),
+                _dev_ptr(digits, self.bits, polys * self._levels * L * n), n, polys, _stream()))
+
+
+def dcrt_external_product_batch(table: _DcrtTable, basis: BigUintApproxSignedBasis, k, key, glwe_in, out, to_coeff=True, scratch=None):
+    """CrtGlwe::mul_dcrt_ggsw_to (primus_lattice/src/glwe/crt.rs:200-227) [+ into_coeff_form] over a batch.
+    key: CUDA [k+1][levels][k+1][L][N]; glwe_in/out: CUDA [batch][k+1][L][N]; scratch: CUDA byte tensor (allocated when None)."""
+    import torch
+    bits, L, n = table.bits, len(table.moduli), table.n
+    batch = glwe_in.numel() // ((k + 1) * L * n)
+    fs = getattr(lib(), f"pfhe_dcrt{bits}_external_product_scratch_bytes")
+    fs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t]; fs.restype = C.c_size_t
+    if scratch is None:
+        need = int(fs(table._h, basis.rns._h, k, basis._log_basis, basis._rev, min(batch, 256) or 1))
+        scratch = torch.empty(max(need, 16), dtype=torch.uint8, device=glwe_in.device)
+    f = getattr(lib(), f"pfhe_dcrt{bits}_external_product_batch")
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                  C.c_void_p, C.c_size_t, C.c_void_p]
+    check(f(table._h, basis.rns._h, k, basis._log_basis, basis._rev, _dev_ptr(key, bits), _dev_ptr(glwe_in, bits),
+            _dev_ptr(out, bits, glwe_in.numel()), batch, int(bool(to_coeff)), C.c_void_p(scratch.data_ptr()), scratch.numel(), _stream()))
+    return scratch
+
+
+def mul_monomial_batch(moduli, degrees, polys, out, log_n, bits=64):
+    """out = polys * X^degree per limb (primus_poly/src/poly/mul.rs:74-99, primus_lattice/src/glwe/crt.rs:76-114).
+    polys/out: CUDA [batch][L][N]; degrees: CUDA uint32/int32 [batch]."""
+    L = len(moduli)
+    m = (_ct(bits) * L)(*[int(x) for x in moduli])
+    batch = polys.numel() // (L << log_n)
+    f = getattr(lib(), f"pfhe_poly{bits}_mul_monomial_batch")
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p]
+    check(f(m, L, _dev_ptr(degrees, 32, batch), _dev_ptr(polys, bits), _dev_ptr(out, bits, polys.numel()), log_n, batch, _stream()))
+
+
+def dot_product_batch(q, a, b, out, n, bits=64):
+    """reduce_dot_product per row (primus_modulus/src/common/compact/slice.rs:371-438). a, b: CUDA [rows][n]; out: CUDA [rows]."""
+    rows = a.numel() // n
+    f = getattr(lib(), f"pfhe_mod{bits}_dot_product_batch")
+    f.argtypes = [_ct(bits), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    check(f(int(q), _dev_ptr(a, bits), _dev_ptr(b, bits, a.numel()), _dev_ptr(out, bits, rows), rows, n, _stream()))
 
 
 def extract_lwe_batch(q, rlwe, lwe, n, bits=64):

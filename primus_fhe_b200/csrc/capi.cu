@@ -12,6 +12,7 @@
 #include "host_math.hpp"
 #include "internal.hpp"
 #include "pfhe.h"
+#include "rns.hpp"
 
 namespace pfhe {
 int lattice_loge(int bits, int log_n);
@@ -408,6 +409,12 @@ struct pfhe_ntt32 : NttHandle<uint32_t> {};
 struct pfhe_ntt64 : NttHandle<uint64_t> {};
 struct pfhe_dcrt32 : DcrtHandle<uint32_t> {};
 struct pfhe_dcrt64 : DcrtHandle<uint64_t> {};
+template <typename T> struct RnsHandle {
+    std::vector<T> moduli;
+    RnsDev<T> base{};  // RNS part only (log_basis = 0); gadget variants are derived per call (a few hundred host cycles)
+};
+struct pfhe_rns32 : RnsHandle<uint32_t> {};
+struct pfhe_rns64 : RnsHandle<uint64_t> {};
 
 namespace pfhe {
 
@@ -509,6 +516,73 @@ static pfhe_status blind_rot(const H *t, uint32_t log_basis, uint32_t levels_in,
     if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
     if (t->dev_lat.loge == 0) return PFHE_ERR_UNSUPPORTED;
     PFHE_CUDA(launch_blind_rotate<T>(t->dev_lat, g, bsk, n_lwe, lwe, tv, acc_out, batch, static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+
+
+template <typename T, typename R> static pfhe_status rns_create(const T *moduli, size_t count, R **out) {
+    if (!out) return PFHE_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!moduli || count == 0) return PFHE_ERR_RNS_EMPTY;
+    auto *h = new (std::nothrow) R();
+    if (!h) return PFHE_ERR_INVALID_ARG;
+    const int rc = make_rns<T>(moduli, count, 0, 0, h->base);
+    if (rc != 0) {
+        delete h;
+        return (pfhe_status)rc;
+    }
+    h->moduli.assign(moduli, moduli + count);
+    *out = h;
+    return PFHE_OK;
+}
+// RnsDev with the gadget part filled in (BigUintApproxSignedBasis::new)
+template <typename T, typename R> static pfhe_status rns_with_gadget(const R *r, uint32_t log_basis, uint32_t levels_in, RnsDev<T> &out) {
+    if (!r || log_basis == 0) return PFHE_ERR_INVALID_ARG;
+    const int rc = make_rns<T>(r->moduli.data(), r->moduli.size(), log_basis, levels_in, out);
+    return (pfhe_status)rc;
+}
+template <typename T> static pfhe_status limb_consts_plain(const T *moduli, size_t limbs, LimbConsts<T> &lc) {
+    return make_limb_consts<T>(moduli, limbs, nullptr, PFHE_OP_MUL, lc);
+}
+
+template <typename T, typename D, typename R>
+static size_t ext_scratch_bytes(const D *t, const R *r, uint32_t k, uint32_t log_basis, uint32_t levels_in, size_t batch) {
+    RnsDev<T> g;
+    if (!t || rns_with_gadget<T>(r, log_basis, levels_in, g) != PFHE_OK) return 0;
+    const size_t n = t->limbs[0]->h.n, L = t->limbs.size();
+    return batch * (size_t)(k + 1) * g.levels * L * n * sizeof(T);
+}
+
+template <typename T, typename D, typename R>
+static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out,
+                                 size_t batch, int to_coeff, void *scratch, size_t scratch_bytes, void *stream) {
+    if (!t || !r || ((!key || !in || !out) && batch)) return PFHE_ERR_INVALID_ARG;
+    if (batch == 0) return PFHE_OK;
+    const size_t L = t->limbs.size(), n = t->limbs[0]->h.n, comps = (size_t)k + 1;
+    if (L != r->moduli.size() || k < 1) return PFHE_ERR_INVALID_ARG;
+    for (size_t i = 0; i < L; i++)
+        if (t->limbs[i]->h.q != r->moduli[i]) return PFHE_ERR_INVALID_ARG;
+    RnsDev<T> g;
+    pfhe_status st = rns_with_gadget<T>(r, log_basis, levels_in, g);
+    if (st != PFHE_OK) return st;
+    LimbConsts<T> lc;
+    if ((st = limb_consts_plain<T>(r->moduli.data(), L, lc)) != PFHE_OK) return st;
+    const size_t per_ct = comps * g.levels * L * n * sizeof(T);
+    if (!scratch || scratch_bytes < per_ct) return PFHE_ERR_INVALID_ARG;
+    const size_t chunk = scratch_bytes / per_ct;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    T *digits = static_cast<T *>(scratch);
+    const size_t glwe_len = comps * L * n;
+    for (size_t done = 0; done < batch; done += chunk) {
+        const size_t nb = batch - done < chunk ? batch - done : chunk;
+        const T *cin = in + done * glwe_len;
+        T *cout = out + done * glwe_len;
+        // digits of every input component: [ct][r][level][limb][n]
+        PFHE_CUDA(launch_rns_gadget<T>(g, cin, digits, n, nb * comps, L * n, (size_t)g.levels * L * n, s));
+        PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)L, digits, digits, nb * comps * g.levels * L, true, s));
+        PFHE_CUDA(launch_rns_key_mac<T>(lc, (int)L, (int)comps, g.levels, digits, key, cout, n, nb, s));
+        if (to_coeff) PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)L, cout, cout, nb * comps * L, false, s));
+    }
     return PFHE_OK;
 }
 
@@ -685,6 +759,82 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     pfhe_status pfhe_extract_lwe##B##_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, void *stream) {                       \
         if ((!rlwe || !lwe) && batch) return PFHE_ERR_INVALID_ARG;                                                                    \
         PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, static_cast<cudaStream_t>(stream)));                                  \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_create(const T *moduli, size_t count, pfhe_rns##B **out) { return rns_create<T>(moduli, count, out); }  \
+    void pfhe_rns##B##_destroy(pfhe_rns##B *r) { delete r; }                                                                          \
+    size_t pfhe_rns##B##_moduli_count(const pfhe_rns##B *r) { return r ? r->moduli.size() : 0; }                                      \
+    size_t pfhe_rns##B##_big_uint_value_len(const pfhe_rns##B *r) { return r ? (size_t)r->base.value_len : 0; }                       \
+    pfhe_status pfhe_rns##B##_moduli_product(const pfhe_rns##B *r, T *out) {                                                          \
+        if (!r || !out) return PFHE_ERR_INVALID_ARG;                                                                                  \
+        for (int i = 0; i < r->base.value_len; i++) out[i] = r->base.product[i];                                                      \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_compose_batch(const pfhe_rns##B *r, const T *residues, T *big, size_t count, void *stream) {            \
+        if (!r || ((!residues || !big) && count)) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_CUDA(launch_rns_compose<T>(r->base, residues, big, count, static_cast<cudaStream_t>(stream)));                           \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_decompose_batch(const pfhe_rns##B *r, const T *big, T *residues, size_t count, void *stream) {          \
+        if (!r || ((!residues || !big) && count)) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_CUDA(launch_rns_decompose<T>(r->base, big, residues, count, static_cast<cudaStream_t>(stream)));                         \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_lift_small_scaled_add_batch(const T *moduli, size_t limbs, T small_modulus, const T *scalars,           \
+                                                          const T *small, T *acc, size_t count, void *stream) {                       \
+        if (!moduli || limbs == 0) return PFHE_ERR_RNS_EMPTY;                                                                         \
+        if (limbs > (size_t)kMaxLimbs || !scalars || ((!small || !acc) && count)) return PFHE_ERR_INVALID_ARG;                        \
+        for (size_t i = 0; i < limbs; i++)                                                                                            \
+            if (moduli[i] <= small_modulus || scalars[i] >= moduli[i] || (moduli[i] >> (sizeof(T) * 8 - 1)) != 0)                     \
+                return PFHE_ERR_INVALID_ARG;                                                                                          \
+        PFHE_CUDA(launch_rns_lift_scaled_acc<T>(moduli, (int)limbs, small_modulus, scalars, small, acc, count,                        \
+                                                static_cast<cudaStream_t>(stream)));                                                  \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_bigbasis##B##_geometry(const pfhe_rns##B *r, uint32_t log_basis, uint32_t levels_in, uint32_t *levels,           \
+                                            uint32_t *drop_bits) {                                                                    \
+        RnsDev<T> g;                                                                                                                  \
+        pfhe_status st = rns_with_gadget<T>(r, log_basis, levels_in, g);                                                              \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if (levels) *levels = g.levels;                                                                                               \
+        if (drop_bits) *drop_bits = g.drop_bits;                                                                                      \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_rns##B##_gadget_decompose_batch(const pfhe_rns##B *r, uint32_t log_basis, uint32_t levels_in, const T *residues, \
+                                                     T *digits, size_t n, size_t polys, void *stream) {                               \
+        RnsDev<T> g;                                                                                                                  \
+        pfhe_status st = rns_with_gadget<T>(r, log_basis, levels_in, g);                                                              \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if ((!residues || !digits) && n * polys) return PFHE_ERR_INVALID_ARG;                                                         \
+        const size_t L = r->moduli.size();                                                                                            \
+        PFHE_CUDA(launch_rns_gadget<T>(g, residues, digits, n, polys, L * n, (size_t)g.levels * L * n,                                \
+                                       static_cast<cudaStream_t>(stream)));                                                           \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    size_t pfhe_dcrt##B##_external_product_scratch_bytes(const pfhe_dcrt##B *t, const pfhe_rns##B *r, uint32_t k, uint32_t log_basis, \
+                                                         uint32_t levels_in, size_t batch) {                                          \
+        return ext_scratch_bytes<T>(t, r, k, log_basis, levels_in, batch);                                                            \
+    }                                                                                                                                 \
+    pfhe_status pfhe_dcrt##B##_external_product_batch(const pfhe_dcrt##B *t, const pfhe_rns##B *r, uint32_t k, uint32_t log_basis,    \
+                                                      uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,            \
+                                                      int to_coeff, void *scratch, size_t scratch_bytes, void *stream) {              \
+        return dcrt_ext_prod<T>(t, r, k, log_basis, levels_in, key, in, out, batch, to_coeff, scratch, scratch_bytes, stream);        \
+    }                                                                                                                                 \
+    pfhe_status pfhe_poly##B##_mul_monomial_batch(const T *moduli, size_t limbs, const uint32_t *degrees, const T *in, T *out,        \
+                                                  uint32_t log_n, size_t batch, void *stream) {                                       \
+        LimbConsts<T> lc;                                                                                                             \
+        pfhe_status st = limb_consts_plain<T>(moduli, limbs, lc);                                                                     \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if (((!degrees || !in || !out) && batch) || in == out || log_n == 0 || log_n > 20) return PFHE_ERR_INVALID_ARG;               \
+        PFHE_CUDA(launch_mul_monomial<T>(lc, (int)limbs, degrees, in, out, log_n, batch, static_cast<cudaStream_t>(stream)));         \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_dot_product_batch(T q, const T *a, const T *b, T *out, size_t rows, size_t n, void *stream) {           \
+        LimbConsts<T> lc;                                                                                                             \
+        pfhe_status st = limb_consts_plain<T>(&q, 1, lc);                                                                             \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if ((!a || !b || !out) && rows) return PFHE_ERR_INVALID_ARG;                                                                  \
+        PFHE_CUDA(launch_dot_product<T>(lc.br[0], a, b, out, rows, n, static_cast<cudaStream_t>(stream)));                            \
         return PFHE_OK;                                                                                                               \
     }
 

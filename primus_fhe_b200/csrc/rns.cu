@@ -11,8 +11,12 @@
 //   reduce_dot_product                                                         primus_modulus/src/common/compact/slice.rs:371-401
 // The L > 1 external product is composed from kernels (digits -> DCRT NTT -> fused MAC -> INTT) with a
 // stream-ordered scratch buffer; the L = 1 case has the fully fused kernel in lattice.cu.
-#include "internal.hpp"
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
 #include "host_math.hpp"
+#include "internal.hpp"
 #include "rns.hpp"
 
 namespace pfhe {

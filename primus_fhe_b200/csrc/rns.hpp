@@ -1,0 +1,43 @@
+// rns.hpp -- RNS base + multi-word gadget basis as one kernel-parameter struct, and the launchers of rns.cu.
+#pragma once
+#include "internal.hpp"
+
+namespace pfhe {
+
+constexpr int kRnsMaxLimbs = 8;  // limbs of an RNS base handled by the compose / gadget kernels
+constexpr int kRnsMaxWords = 8;  // words of the composed value (8 x ~50-bit limbs = 400 bits = 7 u64 words)
+
+// RNSBase (primus_rns/src/base.rs:26-122) + BigUintApproxSignedBasis (primus_decompose/src/big_integer/basis.rs:17-211)
+template <typename T> struct RnsDev {
+    int limbs, value_len;
+    T q[kRnsMaxLimbs];
+    T product[kRnsMaxWords];                 // Q = prod q_i, little endian
+    T punct[kRnsMaxLimbs][kRnsMaxWords];     // Q / q_i
+    T inv_punct[kRnsMaxLimbs], inv_punct_q[kRnsMaxLimbs];  // (Q/q_i)^-1 mod q_i and its Shoup quotient
+    // gadget part (log_basis == 0: RNS base only)
+    uint32_t log_basis, levels, drop_bits;
+    T basis_m1, carry_mask, init_mask;
+    int has_threshold, has_init_mask, init_index;
+    T threshold[kRnsMaxWords], add[kRnsMaxWords];
+};
+
+// status codes mirror pfhe_status: 0 ok, 6 EmptyBase, 7 CoPrimeError, 9 invalid / unsupported size
+template <typename T> int make_rns(const T *moduli, size_t limbs, uint32_t log_basis, uint32_t levels_in, RnsDev<T> &r);
+
+template <typename T> cudaError_t launch_rns_compose(const RnsDev<T> &r, const T *residues, T *big, size_t count, cudaStream_t s);
+template <typename T> cudaError_t launch_rns_decompose(const RnsDev<T> &r, const T *big, T *residues, size_t count, cudaStream_t s);
+template <typename T>
+cudaError_t launch_rns_gadget(const RnsDev<T> &r, const T *residues, T *digits, size_t count, size_t polys, size_t in_stride, size_t out_stride,
+                              cudaStream_t s);
+template <typename T>
+cudaError_t launch_rns_key_mac(const LimbConsts<T> &lc, int limbs, int comps, uint32_t levels, const T *digits, const T *key, T *out, size_t n,
+                               size_t batch, cudaStream_t s);
+template <typename T>
+cudaError_t launch_rns_lift_scaled_acc(const T *moduli, int limbs, T small_modulus, const T *scalars, const T *small, T *acc, size_t count,
+                                       cudaStream_t s);
+template <typename T>
+cudaError_t launch_mul_monomial(const LimbConsts<T> &lc, int limbs, const uint32_t *degrees, const T *in, T *out, uint32_t log_n, size_t batch,
+                                cudaStream_t s);
+template <typename T> cudaError_t launch_dot_product(const Barrett<T> &br, const T *a, const T *b, T *out, size_t rows, size_t n, cudaStream_t s);
+
+}  // namespace pfhe
