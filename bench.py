@@ -41,11 +41,38 @@ Q = 1125899906826241
 BATCH = 65536
 BYTES_PER_NTT = 2 * N * 8            # read + write, SURVEY.md 8(d)
 MODMULS_PER_NTT = (N // 2) * LOG_N   # butterflies
+FP64_PER_NTT = 944 * 256             # FP64 instructions of the lazy-fold kernel: 96 butterflies x 8 + 3 folds x 16 x 3 + 32 conversions, per thread
+FP64_PEAK = 1.75e13                  # measured DFMA/DMUL/DADD rate of one B200 (profiles/r01_ubench_pipes.log)
 METRIC = "NTTs/s at N=4096 (u64 forward negacyclic NTT, batch 65536 per GPU)"
 UNIT = "NTT/s"
 CONFIG = {"workload": "batched forward NTT, N=4096, q=1125899906826241 (50-bit), batch 65536 polys (2 GiB) per GPU, in place",
           "l2": "inputs (2 GiB) exceed L2 (126 MB): no flush needed between timed iterations",
           "sharding": "independent polynomials split across GPUs, no data-path collective"}
+
+
+def _c3_primes():
+    """8 primes just below 2^50 with q = 1 mod 2^15 (config C3)."""
+    def is_prime(n):
+        d, r = n - 1, 0
+        while d % 2 == 0:
+            d //= 2; r += 1
+        for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+            x = pow(a, d, n)
+            if x in (1, n - 1):
+                continue
+            for _ in range(r - 1):
+                x = x * x % n
+                if x == n - 1:
+                    break
+            else:
+                return False
+        return True
+    out, c = [], (1 << 50) - (1 << 15) + 1
+    while len(out) < 8:
+        if is_prime(c):
+            out.append(c)
+        c -= 1 << 15
+    return out
 
 
 def _peaks():
@@ -265,7 +292,10 @@ def main():
                 "peak_source": peak_src, "kernel": "ntt_kernel<u64,N=4096> forward", "algorithmic_bytes_per_launch": batch * BYTES_PER_NTT,
                 "avg_launch_ms": avg_kernel_ms,
                 "modmul": {"butterflies_per_s": batch * MODMULS_PER_NTT / (avg_kernel_ms * 1e-3),
-                           "note": "secondary bound: see DESIGN.md (integer / FP64 pipe butterfly rate measured by pfhe_modmul_microbench)"}}
+                           "fp64_instr_per_ntt": FP64_PER_NTT, "fp64_pipe_peak_instr_per_s": FP64_PEAK,
+                           "frac_of_fp64_pipe": batch * FP64_PER_NTT / (avg_kernel_ms * 1e-3) / FP64_PEAK,
+                           "note": "secondary (binding) bound: q < 2^50 runs on the FP64 pipe, 944 FP64 instructions per thread x 256 "
+                                   "threads per NTT against the measured DFMA rate (profiles/r01_ubench_pipes.log); see DESIGN.md section 4"}}
 
     # ---- CPU baseline (bounded sample) ---------------------------------------------------------------------
     cpu_value, cores, cpu_s = cpu_reference(8192, 3)
@@ -306,6 +336,26 @@ def main():
             tv = torch.randint(0, q32, (1024,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
             acc = torch.empty((nb, 2048), dtype=torch.int32, device="cuda")
             extra["bootstraps_per_s_blind_rotation_n512_N1024_u32"] = nb / timed(lambda: t10.blind_rotate_batch(7, None, bsk, nl, lwe, tv, acc), reps=2)
+            del bsk, lwe, acc, key, cin, cout
+            # C3 RNS polynomial product: N=16384, 8 limbs of ~50-bit primes (q = 1 mod 2^15), fused per limb
+            c3 = _c3_primes()
+            dc = P.U64DcrtTable(14, c3, device=local_rank)
+            nrns = 256
+            ra = torch.stack([torch.randint(0, m, (nrns, 16384), dtype=torch.int64, device="cuda", generator=g) for m in c3], dim=1).contiguous()
+            rb, rc = ra.flip(0).contiguous(), torch.empty_like(ra)
+            extra["rns_polymuls_per_s_n16384_l8_u64"] = nrns / timed(lambda: dc.polymul_batch(ra, rb, rc))
+            del ra, rb, rc
+            # multi-limb external product: N=2048, k=1, L=2 (100-bit Q), base 2^7 (l=14), batch 1024
+            m2 = [Q, 1125899906629633]
+            dc2 = P.U64DcrtTable(11, m2, device=local_rank)
+            bb = P.BigUintApproxSignedBasis(P.RNSBase(m2, 64), 7, None)
+            lv2 = bb.decompose_length()
+            key2 = torch.stack([torch.randint(0, m, (2 * lv2 * 2, 2048), dtype=torch.int64, device="cuda", generator=g) for m in m2], dim=1).contiguous()
+            cin2 = torch.stack([torch.randint(0, m, (1024 * 2, 2048), dtype=torch.int64, device="cuda", generator=g) for m in m2], dim=1).contiguous()
+            cout2 = torch.empty_like(cin2)
+            scratch = P.dcrt_external_product_batch(dc2, bb, 1, key2, cin2, cout2, True)
+            extra["dcrt_external_products_per_s_n2048_L2_l14_u64"] = 1024 / timed(
+                lambda: P.dcrt_external_product_batch(dc2, bb, 1, key2, cin2, cout2, True, scratch=scratch))
         except Exception as ex:  # secondary numbers must never hide the headline
             extra["error"] = repr(ex)
 

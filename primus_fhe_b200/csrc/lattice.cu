@@ -130,8 +130,7 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = F::load(gadget_level<T>(g, adj[j], shift, carry[j]), cx);
-                sync();  // the exchange buffer was last read with the previous transform's final pattern
-                Core::template fwd_from<0>(x, sm, tb, cx, t, sync);
+                Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);  // releases the exchange buffer for the next digit
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
                 const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
@@ -159,8 +158,15 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
     }
 };
 
+// at least 16 warps per SM: caps the allocator at 128 registers for the 256-thread configurations (the freer
+// instruction scheduling after the barrier reduction otherwise grows to ~180 registers and halves the occupancy)
+template <int LOGN, int LOGE, int PPB> constexpr int ep_min_blocks() {
+    constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
+    return threads >= 512 ? 1 : 512 / threads;
+}
+
 template <typename F, int LOGN, int LOGE, int COMPS, int PPB>
-__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB)
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ep_min_blocks<LOGN, LOGE, PPB>())
 external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, const __grid_constant__ GadgetParams<typename F::WordT> g,
                         const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ in,
                         typename F::WordT *__restrict__ out, size_t batch, int to_coeff) {

@@ -506,14 +506,18 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     }
     // forward passes PASS..NPASS-1 with x holding pass PASS's elements on entry; on exit x holds the
     // last pass's elements (thread t owns words [t*E, (t+1)*E)), lazy representation.
-    template <int PASS, typename SyncF>
+    // RELEASE: synchronise the whole group right after the LAST exchange load, i.e. hand the buffer back before the
+    // final register pass -- for callers that run transforms back to back (the next transform's first store then
+    // needs no barrier of its own, and the final pass + whatever follows overlaps other warps' exchanges).
+    template <int PASS, bool RELEASE = false, typename SyncF>
     __device__ __forceinline__ static void fwd_from(Elem (&x)[E], Elem *sm, const DevNtt<T> &tb, const Ctx &c, int t, SyncF sync) {
         fwd_pass_regs<PASS>(x, tb, c, t);
         if constexpr (PASS + 1 < P::NPASS) {
             sm_store<PASS>(x, sm, t);
             xchg_sync<PASS>(sync);
             sm_load<PASS + 1>(x, sm, t);
-            fwd_from<PASS + 1>(x, sm, tb, c, t, sync);
+            if constexpr (RELEASE && PASS + 2 == P::NPASS) sync();
+            fwd_from<PASS + 1, RELEASE>(x, sm, tb, c, t, sync);
         }
     }
     // inverse passes PASS..0 with x holding pass PASS's elements on entry; on exit x holds pass 0's
