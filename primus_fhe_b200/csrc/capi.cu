@@ -157,7 +157,9 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     if (loge_lat) fill_pass_tables<T>(h, loge_lat, fpl, ipl);
     // FP64-pipe path: u64 words and q < 2^50 (every table value is then an exact double)
     const char *no_f64 = getenv("PFHE_DISABLE_F64");
-    const bool use_f64 = BITS == 64 && loge != 0 && ((uint64_t)q >> 50) == 0 && !(no_f64 && no_f64[0] == '1');
+    // lazy-fold exactness budget (tools/f64_bounds.py): q <= 2^50 - 2^10
+    const bool f64_ok = BITS == 64 && (uint64_t)q <= ((uint64_t)1 << 50) - 1024 && !(no_f64 && no_f64[0] == '1');
+    const bool use_f64 = f64_ok && loge != 0;
     if (use_f64) {
         fpf.resize(fp.size());
         ipf.resize(ip.size());
@@ -166,7 +168,7 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
             ipf[i] = (double)ip[i].x;
         }
     }
-    const bool use_f64_lat = BITS == 64 && loge_lat != 0 && ((uint64_t)q >> 50) == 0 && !(no_f64 && no_f64[0] == '1');
+    const bool use_f64_lat = f64_ok && loge_lat != 0;
     if (use_f64_lat) {
         fplf.resize(fpl.size());
         iplf.resize(ipl.size());

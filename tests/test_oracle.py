@@ -295,3 +295,15 @@ def test_golden_fixtures_match_oracle():
         t = cls(case["log_n"], case["q"]); sb = O.ApproxSignedBasis(case["q"], case["log_basis"], None, case["bits"])
         out = O.external_product_single(t, sb, 1, np.array(case["key"], dtype=dt), np.array(case["input"], dtype=dt).reshape(1, -1))
         assert [int(v) for v in out.reshape(-1)] == case["output"]
+
+
+# ---- exactness budget of the lazy FP64 butterflies (product code: primus_fhe_b200/csrc/ntt_core.cuh, F64LazyField) ----------
+def test_f64_lazy_fold_exactness_budget():
+    """Walks every stage schedule the kernels use with exact rationals: quotient range of the magic-constant rounding and
+    integer exactness (< 2^53) of every sum, for the largest admitted modulus (q <= 2^50 - 2^10)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("f64_bounds", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "f64_bounds.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    res = mod.check_all()
+    assert len(res) == 45 and all(f < 8.001 and i < 8.001 for f, i in res.values())   # the hard checks (<= 2^53) are the script's asserts
+    assert mod.QMAX == (1 << 50) - 1024
