@@ -112,7 +112,7 @@ def test_monomial_transforms(bits, log_n, q):
         assert np.array_equal(got[i], want)
 
 
-@pytest.mark.parametrize("bits,log_n,q", [(64, 12, Q50), (64, 13, Q50), (64, 10, Q60), (64, 6, Q50), (32, 10, Q27), (32, 11, Q27), (32, 4, Q27), (64, 14, 1125899904679937), (32, 13, Q27)])
+@pytest.mark.parametrize("bits,log_n,q", [(64, 12, Q50), (64, 13, Q50), (64, 10, Q60), (64, 6, Q50), (32, 10, Q27), (32, 11, Q27), (32, 4, Q27), (64, 14, 1125899904679937), (32, 13, Q27), (64, 13, Q60)])
 def test_polymul_matches_oracle_and_schoolbook(bits, log_n, q):
     import torch
     from oracle import oracle as O
@@ -129,9 +129,17 @@ def test_polymul_matches_oracle_and_schoolbook(bits, log_n, q):
     dc = torch.empty_like(da)
     g.polymul_batch(da, db, dc)
     assert np.array_equal(dc.cpu().numpy().view(dt), want)
-    # aliasing c = a is allowed
+    # aliasing c = a and c = b is allowed; a = b is a squaring
     g.polymul_batch(da, db, da)
     assert np.array_equal(da.cpu().numpy().view(dt), want)
+    da = torch.from_numpy(a.view(sdt)).cuda()
+    g.polymul_batch(da, db, db)
+    assert np.array_equal(db.cpu().numpy().view(dt), want)
+    sq = o.polymul_batch(a, a)
+    g.polymul_batch(da, da, dc)
+    assert np.array_equal(dc.cpu().numpy().view(dt), sq)
+    g.polymul_batch(da, da, da)
+    assert np.array_equal(da.cpu().numpy().view(dt), sq)
     # host shim
     assert np.array_equal(g.polymul_slices(a, b), want)
 
