@@ -339,6 +339,22 @@ pfhe_status pfhe_dcrt32_external_product_batch(const pfhe_dcrt32 *t, const pfhe_
                                                uint32_t levels_in, const uint32_t *key, const uint32_t *in, uint32_t *out, size_t batch,
                                                int to_coeff, void *scratch, size_t scratch_bytes, void *stream);
 
+/* BaseConverter (primus_rns/src/converter.rs:21-365): RNS base change with the precomputed matrix (Q/q_i) mod p_k.
+ * Host-only handle; up to 8 input and 8 output moduli.  Layout: [polys][moduli][n] (modulus-major per polynomial). */
+typedef struct pfhe_baseconv32 pfhe_baseconv32;
+typedef struct pfhe_baseconv64 pfhe_baseconv64;
+pfhe_status pfhe_baseconv64_create(const uint64_t *in_moduli, size_t n_in, const uint64_t *out_moduli, size_t n_out, pfhe_baseconv64 **out);
+pfhe_status pfhe_baseconv32_create(const uint32_t *in_moduli, size_t n_in, const uint32_t *out_moduli, size_t n_out, pfhe_baseconv32 **out);
+void pfhe_baseconv64_destroy(pfhe_baseconv64 *c);
+void pfhe_baseconv32_destroy(pfhe_baseconv32 *c);
+/* BaseConverter::fast_convert_array (converter.rs:186-213): in [polys][n_in][n] -> out [polys][n_out][n] (device). */
+pfhe_status pfhe_baseconv64_fast_convert_batch(const pfhe_baseconv64 *c, const uint64_t *in, uint64_t *out, size_t n, size_t polys, void *stream);
+pfhe_status pfhe_baseconv32_fast_convert_batch(const pfhe_baseconv32 *c, const uint32_t *in, uint32_t *out, size_t n, size_t polys, void *stream);
+/* BaseConverter::exact_convert_array (converter.rs:257-365; exactly one output modulus, else INVALID_ARG):
+ * in [polys][n_in][n] -> out [polys][n]; the floating correction term follows the reference's operation order. */
+pfhe_status pfhe_baseconv64_exact_convert_batch(const pfhe_baseconv64 *c, const uint64_t *in, uint64_t *out, size_t n, size_t polys, void *stream);
+pfhe_status pfhe_baseconv32_exact_convert_batch(const pfhe_baseconv32 *c, const uint32_t *in, uint32_t *out, size_t n, size_t polys, void *stream);
+
 /* Polynomial::mul_monomial_assign / CrtGlwe::mul_monic_monomial_assign (primus_poly/src/poly/mul.rs:74-99,
  * primus_lattice/src/glwe/crt.rs:76-114): out = in * X^degree in Z_q[X]/(X^N+1) per limb; in/out [batch][limbs][N]
  * device (out != in), degrees[batch] device, each taken mod 2N. */

@@ -466,6 +466,45 @@ class RNSBase:
         f(self._h, _ptr(s), _ptr(acc), s.size, int(small_modulus), _ptr(sc)); return acc
 
 
+
+class BaseConverter:
+    """primus_rns/src/converter.rs:21-365: fast_convert_array / exact_convert_array, modulus-major layout."""
+
+    def __init__(self, in_moduli, out_moduli, bits=64):
+        self.bits, self.in_moduli, self.out_moduli = bits, [int(m) for m in in_moduli], [int(m) for m in out_moduli]
+        err = C.c_int(0)
+        f = getattr(lib(), f"o_baseconv_create{bits}"); f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        a, b = _arr(self.in_moduli, bits), _arr(self.out_moduli, bits)
+        self._h = f(_ptr(a), len(self.in_moduli), _ptr(b), len(self.out_moduli), C.byref(err))
+        if not self._h:
+            raise OracleError(err.value)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            f = getattr(lib(), f"o_baseconv_destroy{self.bits}"); f.restype = None; f.argtypes = [C.c_void_p]
+            f(h); self._h = None
+
+    def matrix(self):
+        f = getattr(lib(), f"o_baseconv_matrix{self.bits}"); f.restype = C.POINTER(_ct(self.bits)); f.argtypes = [C.c_void_p]
+        return np.ctypeslib.as_array(f(self._h), shape=(len(self.out_moduli), len(self.in_moduli))).copy()
+
+    def fast_convert_array(self, crt_in, poly_length):
+        x = _arr(crt_in, self.bits); out = np.empty(len(self.out_moduli) * poly_length, dtype=_np(self.bits))
+        f = getattr(lib(), f"o_baseconv_fast_array{self.bits}"); f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        f(self._h, _ptr(x), _ptr(out), poly_length); return out
+
+    def exact_convert_array(self, crt_in, poly_length):
+        x = _arr(crt_in, self.bits); out = np.empty(poly_length, dtype=_np(self.bits))
+        f = getattr(lib(), f"o_baseconv_exact_array{self.bits}"); f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        if f(self._h, _ptr(x), _ptr(out), poly_length) != 0:
+            raise ValueError("output base in exact_convert_array must be one.")
+        return out
+
+
 class BigUintApproxSignedBasis:
     """primus_decompose/src/big_integer/basis.rs:17-434."""
 

@@ -450,6 +450,45 @@ class RNSBase:
                 small.numel(), _stream()))
 
 
+class BaseConverter:
+    """BaseConverter::new(input_base, output_base) (primus_rns/src/converter.rs:21-76) with the array conversions."""
+
+    def __init__(self, in_moduli, out_moduli, bits=64):
+        self.bits, self.in_moduli, self.out_moduli = bits, [int(m) for m in in_moduli], [int(m) for m in out_moduli]
+        self._h = C.c_void_p()
+        self._p = f"pfhe_baseconv{bits}_"
+        a = (_ct(bits) * max(1, len(self.in_moduli)))(*self.in_moduli)
+        b = (_ct(bits) * max(1, len(self.out_moduli)))(*self.out_moduli)
+        f = getattr(lib(), self._p + "create"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(f(a, len(self.in_moduli), b, len(self.out_moduli), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                f = getattr(lib(), self._p + "destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
+
+    def input_moduli_count(self): return len(self.in_moduli)
+    def output_moduli_count(self): return len(self.out_moduli)
+
+    def _run(self, name, crt_in, crt_out, n, out_limbs):
+        polys = crt_in.numel() // (len(self.in_moduli) * n)
+        f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p] * 3 + [C.c_size_t, C.c_size_t, C.c_void_p]
+        check(f(self._h, _dev_ptr(crt_in, self.bits), _dev_ptr(crt_out, self.bits, polys * out_limbs * n), n, polys, _stream()))
+
+    def fast_convert_array(self, crt_in, crt_out, poly_length):
+        """crt_in: CUDA [polys][L_in][n]; crt_out: CUDA [polys][L_out][n] (converter.rs:186-213)."""
+        self._run("fast_convert_batch", crt_in, crt_out, poly_length, len(self.out_moduli))
+
+    def exact_convert_array(self, crt_in, crt_out, poly_length):
+        """crt_in: CUDA [polys][L_in][n]; crt_out: CUDA [polys][n]; one output modulus (converter.rs:257-365)."""
+        self._run("exact_convert_batch", crt_in, crt_out, poly_length, 1)
+
+
 class BigUintApproxSignedBasis:
     """BigUintApproxSignedBasis::new(Q, log_basis, reverse_length) over an RNS base
     (primus_decompose/src/big_integer/basis.rs:17-211) + the fused digit pipeline of the gadget product."""

@@ -415,6 +415,11 @@ template <typename T> struct RnsHandle {
     std::vector<T> moduli;
     RnsDev<T> base{};  // RNS part only (log_basis = 0); gadget variants are derived per call (a few hundred host cycles)
 };
+template <typename T> struct BaseConvHandle {
+    BaseConvDev<T> dev{};
+};
+struct pfhe_baseconv32 : BaseConvHandle<uint32_t> {};
+struct pfhe_baseconv64 : BaseConvHandle<uint64_t> {};
 struct pfhe_rns32 : RnsHandle<uint32_t> {};
 struct pfhe_rns64 : RnsHandle<uint64_t> {};
 
@@ -821,6 +826,33 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
                                                       uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,            \
                                                       int to_coeff, void *scratch, size_t scratch_bytes, void *stream) {              \
         return dcrt_ext_prod<T>(t, r, k, log_basis, levels_in, key, in, out, batch, to_coeff, scratch, scratch_bytes, stream);        \
+    }                                                                                                                                 \
+    pfhe_status pfhe_baseconv##B##_create(const T *in_moduli, size_t n_in, const T *out_moduli, size_t n_out, pfhe_baseconv##B **out) { \
+        if (!out) return PFHE_ERR_INVALID_ARG;                                                                                        \
+        *out = nullptr;                                                                                                               \
+        if (!in_moduli || !out_moduli || n_in == 0 || n_out == 0) return PFHE_ERR_RNS_EMPTY;                                          \
+        auto *h = new (std::nothrow) pfhe_baseconv##B();                                                                              \
+        if (!h) return PFHE_ERR_INVALID_ARG;                                                                                          \
+        const int rc = make_baseconv<T>(in_moduli, n_in, out_moduli, n_out, h->dev);                                                  \
+        if (rc != 0) {                                                                                                                \
+            delete h;                                                                                                                 \
+            return (pfhe_status)rc;                                                                                                   \
+        }                                                                                                                             \
+        *out = h;                                                                                                                     \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    void pfhe_baseconv##B##_destroy(pfhe_baseconv##B *c) { delete c; }                                                                \
+    pfhe_status pfhe_baseconv##B##_fast_convert_batch(const pfhe_baseconv##B *c, const T *in, T *out, size_t n, size_t polys,         \
+                                                      void *stream) {                                                                 \
+        if (!c || ((!in || !out) && n * polys)) return PFHE_ERR_INVALID_ARG;                                                          \
+        PFHE_CUDA(launch_baseconv<T>(c->dev, in, out, n, polys, false, static_cast<cudaStream_t>(stream)));                           \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_baseconv##B##_exact_convert_batch(const pfhe_baseconv##B *c, const T *in, T *out, size_t n, size_t polys,        \
+                                                       void *stream) {                                                                \
+        if (!c || c->dev.n_out != 1 || ((!in || !out) && n * polys)) return PFHE_ERR_INVALID_ARG;                                     \
+        PFHE_CUDA(launch_baseconv<T>(c->dev, in, out, n, polys, true, static_cast<cudaStream_t>(stream)));                            \
+        return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_poly##B##_mul_monomial_batch(const T *moduli, size_t limbs, const uint32_t *degrees, const T *in, T *out,        \
                                                   uint32_t log_n, size_t batch, void *stream) {                                       \

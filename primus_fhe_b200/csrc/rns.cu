@@ -231,6 +231,55 @@ __global__ void __launch_bounds__(256) dot_product_kernel(const Barrett<T> br, c
     if (threadIdx.x == 0) out[row] = partial[0];
 }
 
+
+// ---- BaseConverter (primus_rns/src/converter.rs) ------------------------------------------------------------------
+// One thread per coefficient: adjusted residues y_i = x_i * (Q/q_i)^-1 mod q_i (converter.rs:141-184), then one lazy
+// double-word dot product per output modulus (converter.rs:203-212; <= 8 terms, no intermediate reduction needed).
+// EXACT (converter.rs:257-365): the floating correction v = trunc(sum_i (double)y_i / (double)q_i + 0.5) is evaluated
+// with the reference's operation order (IEEE division, sequential sum), so the result is bit-identical to the CPU path.
+template <typename T> __device__ __forceinline__ double word_to_double(T v);
+template <> __device__ __forceinline__ double word_to_double<uint32_t>(uint32_t v) { return __uint2double_rn(v); }
+template <> __device__ __forceinline__ double word_to_double<uint64_t>(uint64_t v) { return __ull2double_rn(v); }
+template <typename T> __device__ __forceinline__ T double_to_word(double v);
+template <> __device__ __forceinline__ uint32_t double_to_word<uint32_t>(double v) { return __double2uint_rz(v); }
+template <> __device__ __forceinline__ uint64_t double_to_word<uint64_t>(double v) { return __double2ull_rz(v); }
+
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(256) baseconv_kernel(const __grid_constant__ BaseConvDev<T> c, const T *__restrict__ in, T *__restrict__ out,
+                                                       size_t n, size_t polys) {
+    using W = typename WideOf<T>::type;
+    const size_t total = polys * n;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = gid / n, j = gid % n;
+        const T *x = in + p * (size_t)c.n_in * n + j;
+        T y[kRnsMaxLimbs];
+        double agg = 0.0;
+#pragma unroll
+        for (int i = 0; i < kRnsMaxLimbs; i++) {
+            if (i < c.n_in) {
+                const T xi = x[(size_t)i * n];
+                y[i] = c.inv[i] == 1 ? barrett_reduce_wide(c.in_br[i], xi, (T)0) : shoup<T>(xi, c.inv[i], c.inv_q[i], c.in_br[i].q);
+                if (EXACT) agg = __dadd_rn(agg, __ddiv_rn(word_to_double<T>(y[i]), c.q_f[i]));
+            }
+        }
+        const int n_out = EXACT ? 1 : c.n_out;
+        for (int k = 0; k < n_out; k++) {
+            W acc = 0;
+#pragma unroll
+            for (int i = 0; i < kRnsMaxLimbs; i++)
+                if (i < c.n_in) acc += (W)y[i] * c.matrix[k][i];
+            T r = barrett_reduce_wide(c.out_br[k], (T)acc, (T)(acc >> (sizeof(T) * 8)));
+            if (EXACT) {
+                const T v = double_to_word<T>(__dadd_rn(agg, 0.5));
+                r = mod_sub<T>(r, barrett_mul<T>(c.out_br[0], v, c.q_mod_p[0]), c.out_br[0].q);
+                out[p * n + j] = r;
+            } else {
+                out[(p * (size_t)c.n_out + k) * n + j] = r;
+            }
+        }
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 template <typename T> static void hbig_mul_word(std::vector<T> &a, T v) {
     using W = typename host::Wide<T>::type;
@@ -404,6 +453,53 @@ template <typename T> int make_rns(const T *moduli, size_t limbs, uint32_t log_b
 }
 template int make_rns<uint32_t>(const uint32_t *, size_t, uint32_t, uint32_t, RnsDev<uint32_t> &);
 template int make_rns<uint64_t>(const uint64_t *, size_t, uint32_t, uint32_t, RnsDev<uint64_t> &);
+
+
+template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T *out_moduli, size_t n_out, BaseConvDev<T> &c) {
+    constexpr int B = host::Wide<T>::BITS;
+    memset(&c, 0, sizeof(c));
+    RnsDev<T> in, outb;
+    int rc = make_rns<T>(in_moduli, n_in, 0, 0, in);
+    if (rc) return rc;
+    if ((rc = make_rns<T>(out_moduli, n_out, 0, 0, outb)) != 0) return rc;  // the output base is an RNSBase too
+    c.n_in = (int)n_in;
+    c.n_out = (int)n_out;
+    for (size_t i = 0; i < n_in; i++) {
+        if ((in_moduli[i] >> (B - 2)) != 0) return 5;  // BarrettModulus range
+        c.inv[i] = in.inv_punct[i];
+        c.inv_q[i] = in.inv_punct_q[i];
+        c.in_br[i].q = in_moduli[i];
+        host::barrett_ratio<T>(in_moduli[i], c.in_br[i].r0, c.in_br[i].r1);
+        c.q_f[i] = (double)in_moduli[i];
+    }
+    std::vector<T> prod(in.product, in.product + in.value_len);
+    for (size_t k = 0; k < n_out; k++) {
+        if ((out_moduli[k] >> (B - 2)) != 0) return 5;
+        c.out_br[k].q = out_moduli[k];
+        host::barrett_ratio<T>(out_moduli[k], c.out_br[k].r0, c.out_br[k].r1);
+        for (size_t i = 0; i < n_in; i++) {
+            std::vector<T> p(in.punct[i], in.punct[i] + in.value_len);
+            c.matrix[k][i] = hbig_mod_word<T>(p, out_moduli[k]);
+        }
+        c.q_mod_p[k] = hbig_mod_word<T>(prod, out_moduli[k]);
+    }
+    return 0;
+}
+template int make_baseconv<uint32_t>(const uint32_t *, size_t, const uint32_t *, size_t, BaseConvDev<uint32_t> &);
+template int make_baseconv<uint64_t>(const uint64_t *, size_t, const uint64_t *, size_t, BaseConvDev<uint64_t> &);
+
+template <typename T>
+cudaError_t launch_baseconv(const BaseConvDev<T> &c, const T *in, T *out, size_t n, size_t polys, bool exact, cudaStream_t s) {
+    if (!n || !polys) return cudaSuccess;
+    if (exact)
+        baseconv_kernel<T, true><<<grid_for(n * polys, 256), 256, 0, s>>>(c, in, out, n, polys);
+    else
+        baseconv_kernel<T, false><<<grid_for(n * polys, 256), 256, 0, s>>>(c, in, out, n, polys);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_baseconv<uint32_t>(const BaseConvDev<uint32_t> &, const uint32_t *, uint32_t *, size_t, size_t, bool, cudaStream_t);
+template cudaError_t launch_baseconv<uint64_t>(const BaseConvDev<uint64_t> &, const uint64_t *, uint64_t *, size_t, size_t, bool, cudaStream_t);
 
 template <typename T> cudaError_t launch_rns_compose(const RnsDev<T> &r, const T *residues, T *big, size_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;

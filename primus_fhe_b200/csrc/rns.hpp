@@ -21,6 +21,19 @@ template <typename T> struct RnsDev {
     T threshold[kRnsMaxWords], add[kRnsMaxWords];
 };
 
+// BaseConverter (primus_rns/src/converter.rs:21-365): input base + output moduli + (Q/q_i) mod p_k matrix
+template <typename T> struct BaseConvDev {
+    int n_in, n_out;
+    T inv[kRnsMaxLimbs], inv_q[kRnsMaxLimbs];      // (Q/q_i)^-1 mod q_i and its Shoup quotient
+    Barrett<T> in_br[kRnsMaxLimbs], out_br[kRnsMaxLimbs];
+    T matrix[kRnsMaxLimbs][kRnsMaxLimbs];          // [output k][input i]
+    T q_mod_p[kRnsMaxLimbs];
+    double q_f[kRnsMaxLimbs];
+};
+template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T *out_moduli, size_t n_out, BaseConvDev<T> &c);
+template <typename T>
+cudaError_t launch_baseconv(const BaseConvDev<T> &c, const T *in, T *out, size_t n, size_t polys, bool exact, cudaStream_t s);
+
 // status codes mirror pfhe_status: 0 ok, 6 EmptyBase, 7 CoPrimeError, 9 invalid / unsupported size
 template <typename T> int make_rns(const T *moduli, size_t limbs, uint32_t log_basis, uint32_t levels_in, RnsDev<T> &r);
 

@@ -220,3 +220,56 @@ def test_dot_product_matches_oracle(bits, q, n):
     out = torch.empty(rows, dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
     P.dot_product_batch(q, _dev(a), _dev(b), out, n, bits)
     assert np.array_equal(_host(out, dt), want)
+
+
+@pytest.mark.parametrize("bits,in_m,out_m", [(64, [17, 19, 23], [29, 31]), (64, [Q50, Q50B, Q49], [1152921504606830593, 1125899904679937]),
+                                             (32, [P27A, P27B], [Q27, 268369921]), (64, "c3", [Q50B, Q49, Q50]), (64, [Q50], [Q50B, Q49]),
+                                             (64, [Q50, Q50B], [Q49])])
+def test_base_converter_matches_oracle(bits, in_m, out_m):
+    """BaseConverter::fast_convert_array / exact_convert_array (primus_rns/src/converter.rs:186-365); the oracle is pinned on
+    the reference's deterministic case primus_rns/tests/rns.rs:281-345 (tests/test_oracle.py)."""
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    in_m = _c3_primes() if in_m == "c3" else in_m
+    dt = np.uint64 if bits == 64 else np.uint32
+    tdt = torch.int64 if bits == 64 else torch.int32
+    rng = np.random.default_rng(44)
+    n, polys = 256, 3
+    cin = np.stack([_rand_res(rng, in_m, n, dt) for _ in range(polys)])                 # [polys][L_in][n]
+    oc, gc = O.BaseConverter(in_m, out_m, bits), P.BaseConverter(in_m, out_m, bits)
+    want = np.stack([oc.fast_convert_array(cin[p].reshape(-1), n).reshape(len(out_m), n) for p in range(polys)])
+    out = torch.empty(polys * len(out_m) * n, dtype=tdt, device="cuda")
+    gc.fast_convert_array(_dev(cin), out, n)
+    assert np.array_equal(_host(out, dt).reshape(want.shape), want)
+    o1, g1 = O.BaseConverter(in_m, out_m[:1], bits), P.BaseConverter(in_m, out_m[:1], bits)
+    want1 = np.stack([o1.exact_convert_array(cin[p].reshape(-1), n) for p in range(polys)])
+    out1 = torch.empty(polys * n, dtype=tdt, device="cuda")
+    g1.exact_convert_array(_dev(cin), out1, n)
+    assert np.array_equal(_host(out1, dt).reshape(want1.shape), want1)
+    if len(out_m) > 1:
+        with pytest.raises(P.PfheError):
+            gc.exact_convert_array(_dev(cin), out1, n)
+
+
+def test_base_converter_reference_case():
+    """The reference's own deterministic vectors (primus_rns/tests/rns.rs:281-345), straight through the C-ABI."""
+    import torch
+    import primus_fhe_b200 as P
+    in_m, out_m = [17, 19, 23], [29, 31]
+    by_value = [[0, 0, 0], [1, 2, 3], [16, 18, 22], [7, 11, 13], [4, 0, 19]]
+    n = len(by_value)
+    crt_in = np.array([[r[i] for r in by_value] for i in range(3)], dtype=np.uint64)
+    Q = 17 * 19 * 23
+    out = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    P.BaseConverter(in_m, out_m).fast_convert_array(_dev(crt_in), out, n)
+    got = _host(out, np.uint64).reshape(2, n)
+    for vi, res in enumerate(by_value):
+        y = [res[i] * pow(Q // in_m[i], -1, in_m[i]) % in_m[i] for i in range(3)]
+        for k, p in enumerate(out_m):
+            assert int(got[k, vi]) == sum(y[i] * ((Q // in_m[i]) % p) for i in range(3)) % p
+    vals = [0, 1, 2, 7, 16]
+    ex_in = np.array([vals] * 3, dtype=np.uint64)
+    ex = torch.empty(len(vals), dtype=torch.int64, device="cuda")
+    P.BaseConverter(in_m, [37]).exact_convert_array(_dev(ex_in), ex, len(vals))
+    assert [int(v) for v in _host(ex, np.uint64)] == [v % 37 for v in vals]

@@ -307,3 +307,50 @@ def test_f64_lazy_fold_exactness_budget():
     res = mod.check_all()
     assert len(res) == 45 and all(f < 8.001 and i < 8.001 for f, i in res.values())   # the hard checks (<= 2^53) are the script's asserts
     assert mod.QMAX == (1 << 50) - 1024
+
+
+# ---- BaseConverter: the reference's deterministic case (primus_rns/tests/rns.rs:281-345) + big-int model ---------------
+def test_base_converter_reference_case_and_model():
+    in_m, out_m = [17, 19, 23], [29, 31]
+    by_value = [[0, 0, 0], [1, 2, 3], [16, 18, 22], [7, 11, 13], [4, 0, 19]]
+    n = len(by_value)
+    crt_in = np.array([[r[i] for r in by_value] for i in range(3)], dtype=np.uint64).reshape(-1)
+    conv = O.BaseConverter(in_m, out_m)
+    Q = 17 * 19 * 23
+    assert [[int(v) for v in row] for row in conv.matrix()] == [[(Q // q) % p for q in in_m] for p in out_m]   # converter.rs:57-66
+    out = conv.fast_convert_array(crt_in, n).reshape(2, n)
+    for vi, res in enumerate(by_value):      # scalar fast_convert formula (converter.rs:111-137)
+        y = [res[i] * pow(Q // in_m[i], -1, in_m[i]) % in_m[i] for i in range(3)]
+        for k, p in enumerate(out_m):
+            assert int(out[k, vi]) == sum(y[i] * ((Q // in_m[i]) % p) for i in range(3)) % p
+    # exact conversion on small canonical values == trivial modulo reduction (rns.rs:327-344)
+    ex = O.BaseConverter(in_m, [37])
+    vals = [0, 1, 2, 7, 16]
+    exact_in = np.array([[v] * len(vals) for v in [0]], dtype=np.uint64)  # placeholder, rebuilt below
+    exact_in = np.array([[v for v in vals] for _ in range(3)], dtype=np.uint64).reshape(-1)
+    assert [int(v) for v in ex.exact_convert_array(exact_in, len(vals))] == [v % 37 for v in vals]
+    with pytest.raises(ValueError):
+        conv.exact_convert_array(crt_in, n)
+    # larger bases: fast conversion equals x + alpha*Q (0 <= alpha < L) mod p; exact conversion equals the centred lift mod p
+    rng = np.random.default_rng(77)
+    for bits, im, om in [(64, [Q50, Q50B, Q49], [Q60, 1125899904679937]), (32, [134215681, 134176769], [Q27, Q28])]:
+        dt = np.uint64 if bits == 64 else np.uint32
+        c = O.BaseConverter(im, om, bits)
+        Qb = int(np.prod([int(m) for m in im], dtype=object))
+        n = 300
+        xs = [int(rng.integers(0, 1 << 62)) * int(rng.integers(0, 1 << 62)) * int(rng.integers(0, 1 << 62)) % Qb for _ in range(n)]
+        xs[0], xs[1], xs[2] = 0, 1, Qb - 1
+        cin = np.array([[x % m for x in xs] for m in im], dtype=np.uint64).astype(dt).reshape(-1)
+        out = c.fast_convert_array(cin, n).reshape(len(om), n)
+        for j, x in enumerate(xs):
+            y = [(x % m) * pow(Qb // m, -1, m) % m for m in im]
+            full = sum(yi * (Qb // m) for yi, m in zip(y, im))
+            assert full % Qb == x and 0 <= (full - x) // Qb < len(im)
+            for k, p in enumerate(om):
+                assert int(out[k, j]) == full % p
+        c1 = O.BaseConverter(im, om[:1], bits)
+        ex = c1.exact_convert_array(cin, n)
+        for j, x in enumerate(xs):
+            if Qb // 8 < x < 3 * Qb // 8 or 5 * Qb // 8 < x < 7 * Qb // 8:   # away from the rounding boundary Q/2 (float correction term)
+                centred = x if x < Qb // 2 else x - Qb
+                assert int(ex[j]) == centred % om[0]
