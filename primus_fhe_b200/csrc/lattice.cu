@@ -58,6 +58,11 @@ template <> struct LatAcc<IntField<uint32_t>> {
     __device__ __forceinline__ static void renorm(Acc &a, const F::Ctx &c) { a = barrett_reduce_wide(c.br, (uint32_t)a, (uint32_t)(a >> 32)); }
     __device__ __forceinline__ static uint32_t final(const Acc &a, const F::Ctx &c) { return barrett_reduce_wide(c.br, (uint32_t)a, (uint32_t)(a >> 32)); }
 };
+// wide forward outputs (< 2^32) go straight into the double-word sums: 16 * (2 log2 N + 1) * q^2 < 2^64 is checked on the host
+template <> struct LatAcc<IntWide32Field> : LatAcc<IntField<uint32_t>> {
+    using F = IntWide32Field;
+    __device__ __forceinline__ static uint32_t prepare(uint32_t x, const F::Ctx &) { return x; }
+};
 template <> struct LatAcc<IntField<uint64_t>> {
     using F = IntField<uint64_t>;
     using Acc = Wide2<uint64_t>;
@@ -324,11 +329,22 @@ static cudaError_t run_br_f(const DevNtt<typename F::WordT> &tb, const GadgetPar
 }
 
 
+// IntWide32Field preconditions: forward values stay below 2^32 and 16 lazy products below 2^64
+static bool wide32_ok(uint64_t q, int logn) {
+    static const bool off = getenv("PFHE_DISABLE_WIDE32") != nullptr;  // A/B tuning hook
+    const uint64_t growth = 2 * (uint64_t)logn + 1;
+    if (off || growth * q >= ((uint64_t)1 << 32)) return false;
+    const unsigned __int128 worst = (unsigned __int128)16 * growth * q * q;
+    return (worst >> 64) == 0;
+}
+
 template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
 static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
                           cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
         if (tb.use_f64) return run_ep_f<F64Field, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
+    } else {
+        if (wide32_ok(tb.q, LOGN)) return run_ep_f<IntWide32Field, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
     }
     return run_ep_f<IntField<T>, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
 }
@@ -337,6 +353,8 @@ static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T
                           T *acc_out, size_t batch, cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
         if (tb.use_f64) return run_br_f<F64Field, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
+    } else {
+        if (wide32_ok(tb.q, LOGN)) return run_br_f<IntWide32Field, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
     }
     return run_br_f<IntField<T>, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
 }

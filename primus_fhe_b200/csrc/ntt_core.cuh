@@ -184,6 +184,27 @@ template <typename T> struct IntField {
     __device__ __forceinline__ static Elem mac_bits(T v, const Ctx &) { return v; }
 };
 
+
+// Integer pipe, u32 words, forward transforms WITHOUT the per-stage conditional subtraction: the Harvey forward
+// butterfly (prime32/scalar/arithmetic.rs:32-41) first folds X from [0,4q) to [0,2q); the Shoup product accepts any
+// 32-bit Y, so when (2*log2(N) + 1) * q < 2^32 the fold can simply be dropped -- values grow by 2q per stage and never
+// wrap (5 instead of 7 instructions per butterfly).  Used by the lattice kernels for digit transforms, whose outputs
+// feed double-word multiply-accumulates that need no canonical input; inverse transforms are those of IntField.
+struct IntWide32Field : IntField<uint32_t> {
+    __device__ __forceinline__ static void fwd(Elem &x, Elem &y, const Tw &w, const Ctx &c, int = 0) {
+        const uint32_t t = shoup_lazy<uint32_t>(y, w.x, w.y, c.q);
+        y = x + c.two_q - t;
+        x = x + t;
+    }
+    // any 32-bit value -> [0, q): one Barrett step with floor(2^32 / q) (= high word of the two-word ratio)
+    __device__ __forceinline__ static uint32_t fwd_word(Elem v, const Ctx &c) {
+        const uint32_t k = __umulhi(v, c.br.r1);
+        return csub<uint32_t>(csub<uint32_t>(v - k * c.q, c.two_q), c.q);
+    }
+    __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return fwd_word(v, c); }
+    __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return barrett_mul<uint32_t>(c.br, fwd_word(a, c), fwd_word(b, c)); }
+};
+
 // FP64 pipe (B200 keeps full-rate FP64: 64 DFMA/clk/SM, while a 64x64-bit integer product costs ~4 half-rate
 // IMAD.WIDE).  Values are integers held exactly in doubles, |v| < 2q < 2^51; q < 2^50.
 //   mulmod(y, w): P = y*w as (h, l) = (RN(P), P - h)  [exact, fma];  c = rint(h * RN(1/q))  [magic-constant rounding];
