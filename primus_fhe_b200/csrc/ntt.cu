@@ -10,7 +10,10 @@
 // One polynomial per thread group (TPP threads); a CTA carries PPB groups. Each polynomial is read from
 // HBM once and written once; everything in between lives in registers / shared memory.
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
+
+#include <cuda.h>
 
 #include "internal.hpp"
 #include "host_math.hpp"
@@ -92,7 +95,54 @@ template <typename F, int LOGN, int LOGE, int PPB> constexpr int polymul_min_blo
     return (need <= 128 && threads < 512) ? 512 / threads : 1;
 }
 
-template <typename F, int LOGN, int LOGE, int PPB, bool FWD>
+// ---- TMA plumbing -------------------------------------------------------------------------------------------------
+// Where a thread's row of the exchange buffer is 128 bytes (u64 with E = 16, u32 with E = 32) the buffer's XOR swizzle is
+// exactly the SWIZZLE_128B pattern of a tensor map with box {E words, N/E rows}.  One elected thread then moves a whole
+// polynomial between the swizzled buffer and its linear image in HBM with a single cp.async.bulk.tensor:
+//   * store: replaces re-reading the buffer (LDS.128) + STG.128 and, above all, the store drain before the CTA can
+//     retire -- the CTA only waits until the TMA unit has READ shared memory (wait_group.read);
+//   * load (inverse input, arrives in bit-reversed = contiguous-per-thread order): replaces LDG.128 + STS.128 + a barrier.
+// Measured on the headline kernel: 52.2 -> 61.4 M NTT/s (profiles/r01_ntt_kernel_experiments.md).
+struct IoMaps {
+    CUtensorMap in, out;
+    const void *src;  // forward input (plain pointer: the forward transform reads with LDG)
+};
+template <typename T, int E> constexpr bool tma_row() { return sizeof(T) * E == 128; }
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// elected thread: shared (swizzled) -> global tensor rows [row, row + N/E); returns once shared memory has been read
+__device__ __forceinline__ void tma_store_poly(const CUtensorMap *map, const void *sm, uint32_t row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0u), "r"(row), "r"(smem_addr(sm))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// elected thread: global tensor rows -> shared (swizzled), completion on the mbarrier
+__device__ __forceinline__ void tma_load_poly(const CUtensorMap *map, void *sm, uint32_t row, uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(sm)),
+                 "l"(map), "r"(0u), "r"(row), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// ---- LSU-path kernels (every configuration) ----------------------------------------------------------------------------
+// PARAM_TB (forward, single modulus): table constants are read straight from the kernel-parameter bank instead of a
+// by-value copy (measured +5..15 % on the forward LSU path; the inverse and the fused product are faster with the copy).
+template <typename F, int LOGN, int LOGE, int PPB, bool FWD, bool PARAM_TB = false>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ntt_min_blocks<F, LOGN, LOGE, PPB>())
 ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
            const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
@@ -109,7 +159,9 @@ ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<t
         if (TPP == 32) return;  // warp-private group: nothing to synchronise with
         poly = npolys - 1;
     }
-    const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
+    DevNtt<T> tb_copy;
+    if (!PARAM_TB) tb_copy = pick_table(tb0, tables, limbs, poly);
+    const DevNtt<T> &tb = PARAM_TB ? tb0 : tb_copy;
     const typename F::Ctx c = F::ctx(tb);
     const T *g_in = src + poly * N;
     T *g_out = dst + poly * N;
@@ -159,6 +211,98 @@ polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     if (active) Core::inv_regs_to_global(xa, cc + poly * N, c, t);
 }
 
+
+// ---- TMA variants (128-byte exchange-buffer rows only) -------------------------------------------------------------
+// MULTI: per-limb tables (DCRT) are picked from the device array; otherwise every table constant is read straight from
+// the kernel-parameter bank (no registers, no loads).
+template <typename F, int LOGN, int LOGE, int PPB, bool FWD, bool MULTI>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ntt_min_blocks<F, LOGN, LOGE, PPB>())
+ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
+               size_t npolys, const __grid_constant__ IoMaps maps) {
+    using Core = NttCore<F, LOGN, LOGE>;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
+    static_assert(tma_row<T, E>(), "TMA path needs 128-byte exchange-buffer rows");
+    extern __shared__ __align__(1024) unsigned char smem_tma[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    Elem *sm = reinterpret_cast<Elem *>(smem_tma) + (size_t)grp * N;
+    size_t poly = (size_t)blockIdx.x * PPB + grp;
+    const bool active = poly < npolys;
+    if (!active) {
+        if (TPP == 32) return;  // warp-private group: nothing to synchronise with
+        poly = npolys - 1;
+    }
+    DevNtt<T> tb_limb;
+    if (MULTI) tb_limb = tables[poly % (size_t)limbs];
+    const DevNtt<T> &tb = MULTI ? tb_limb : tb0;
+    const typename F::Ctx c = F::ctx(tb);
+    const uint32_t row = (uint32_t)(poly * (N / E));
+    typename SyncFor<TPP>::type sync;
+    Elem x[E];
+    if (FWD) {
+        // input: strided coalesced LDG (a bulk-TMA copy-in measured no faster); output: one tensor store
+        Core::forward_g2r(reinterpret_cast<const T *>(maps.src) + poly * N, x, sm, tb, c, t, sync);
+        if (active) Core::fwd_regs_to_sm(x, sm, c, t);
+    } else {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem_tma + sizeof(T) * PPB * N) + grp;
+        if (t == 0) {
+            mbar_init(bar, 1);
+            tma_load_poly(&maps.in, sm, row, bar, (uint32_t)(sizeof(T) * N));
+        }
+        sync();  // barrier initialised before anyone polls it
+        mbar_wait(bar, 0);
+        Core::template sm_load<Core::P::NPASS - 1>(x, sm, t);
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = F::load_bits(x[j], c);
+        Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, c, t, sync);
+        // canonical words back into the slots this thread just read (pass-0 pattern, no hazard)
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = F::inv_bits(x[j], c);
+        if (active) Core::template sm_store<0>(x, sm, t);
+    }
+    fence_async_smem();
+    sync();
+    if (active && t == 0) tma_store_poly(&maps.out, sm, row);
+}
+
+template <typename F, int LOGN, int LOGE, int PPB, bool MULTI>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, polymul_min_blocks<F, LOGN, LOGE, PPB>())
+polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
+                   const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, size_t npolys,
+                   const __grid_constant__ CUtensorMap out_map) {
+    using Core = NttCore<F, LOGN, LOGE>;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
+    extern __shared__ __align__(1024) unsigned char smem_tma[];
+    const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
+    Elem *sm = reinterpret_cast<Elem *>(smem_tma) + (size_t)grp * N;
+    size_t poly = (size_t)blockIdx.x * PPB + grp;
+    const bool active = poly < npolys;
+    if (!active) {
+        if (TPP == 32) return;
+        poly = npolys - 1;
+    }
+    DevNtt<T> tb_limb;
+    if (MULTI) tb_limb = tables[poly % (size_t)limbs];
+    const DevNtt<T> &tb = MULTI ? tb_limb : tb0;
+    const typename F::Ctx c = F::ctx(tb);
+    typename SyncFor<TPP>::type sync;
+    Elem xa[E], xb[E];
+    Core::forward_g2r(a + poly * N, xa, sm, tb, c, t, sync);
+    sync();  // the exchange buffer is reused with the first pass's pattern
+    Core::forward_g2r(b + poly * N, xb, sm, tb, c, t, sync);
+#pragma unroll
+    for (int j = 0; j < E; j++) xa[j] = F::pointwise(xa[j], xb[j], c);
+    Core::template inv_from<Core::P::NPASS - 1>(xa, sm, tb, c, t, sync);
+#pragma unroll
+    for (int j = 0; j < E; j++) xa[j] = F::inv_bits(xa[j], c);
+    if (active) Core::template sm_store<0>(xa, sm, t);
+    fence_async_smem();
+    sync();
+    if (active && t == 0) tma_store_poly(&out_map, sm, (uint32_t)(poly * (N / E)));
+}
 
 // ------------------------------------------------------------------------------------------------
 // generic radix-2 kernel: any 1 <= log_n that fits shared memory (sizes without a register-pass
@@ -290,6 +434,36 @@ __global__ void monomial_kernel(const __grid_constant__ DevNtt<T> tb, T coeff, T
 // ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+
+// tensor map over a batch of polynomials viewed as rows of E words: {E, npolys * N/E}, box {E, N/E}, SWIZZLE_128B
+template <typename T> static bool make_poly_map(CUtensorMap *map, const T *base, size_t npolys, int log_n, int log_e) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    const uint64_t rows = (uint64_t)1 << (log_n - log_e), total_rows = (uint64_t)npolys * rows;
+    const uint64_t e = (uint64_t)1 << log_e;
+    if (!enc || total_rows > 0xffffffffull || rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)e, (cuuint64_t)total_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(e * sizeof(T))};
+    const cuuint32_t box[2] = {(cuuint32_t)e, (cuuint32_t)rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<T *>(base), gdim, gstride, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename F, int LOGN, int LOGE, int PPB>
 static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<typename F::WordT> *tables, int limbs,
                              const typename F::WordT *src, typename F::WordT *dst, size_t npolys, bool fwd, cudaStream_t stream) {
@@ -298,7 +472,31 @@ static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
     cudaError_t e;
-    if (fwd) {
+    if constexpr (tma_row<T, (1 << LOGE)>() && (1 << (LOGN - LOGE)) <= 256) {
+        static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;  // A/B tuning hook
+        IoMaps maps;
+        maps.src = src;
+        if (use_tma && make_poly_map<T>(&maps.out, dst, npolys, LOGN, LOGE) && (fwd || make_poly_map<T>(&maps.in, src, npolys, LOGN, LOGE))) {
+            if (fwd) memset(&maps.in, 0, sizeof(maps.in));
+            auto launch = [&](auto k, size_t bytes) -> cudaError_t {
+                if (bytes > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+                k<<<grid, threads, bytes, stream>>>(tb0, tables, limbs, npolys, maps);
+                count_launch();
+                return cudaGetLastError();
+            };
+            if (limbs > 1) {
+                if (fwd) return launch(ntt_tma_kernel<F, LOGN, LOGE, PPB, true, true>, smem);
+                return launch(ntt_tma_kernel<F, LOGN, LOGE, PPB, false, true>, smem + 8 * PPB);
+            }
+            if (fwd) return launch(ntt_tma_kernel<F, LOGN, LOGE, PPB, true, false>, smem);
+            return launch(ntt_tma_kernel<F, LOGN, LOGE, PPB, false, false>, smem + 8 * PPB);
+        }
+    }
+    if (fwd && limbs <= 1) {
+        auto k = ntt_kernel<F, LOGN, LOGE, PPB, true, true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
+    } else if (fwd) {
         auto k = ntt_kernel<F, LOGN, LOGE, PPB, true>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, src, dst, npolys);
@@ -318,14 +516,27 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
-    auto k = polymul_kernel<F, LOGN, LOGE, PPB>;
     cudaError_t e;
+    if constexpr (tma_row<T, (1 << LOGE)>() && (1 << (LOGN - LOGE)) <= 256) {
+        static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;
+        CUtensorMap map;
+        if (use_tma && make_poly_map<T>(&map, c, npolys, LOGN, LOGE)) {
+            auto launch = [&](auto k) -> cudaError_t {
+                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, npolys, map);
+                count_launch();
+                return cudaGetLastError();
+            };
+            if (limbs > 1) return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, true>);
+            return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, false>);
+        }
+    }
+    auto k = polymul_kernel<F, LOGN, LOGE, PPB>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
     count_launch();
     return cudaGetLastError();
 }
-
 
 // field selection: u64 tables with q < 2^50 run on the FP64 pipe, everything else on the integer pipe.
 // PFHE_F64_LAZY=0 selects the per-stage-fold FP64 butterflies (A/B tuning hook).

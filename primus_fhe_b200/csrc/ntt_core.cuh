@@ -177,6 +177,7 @@ template <typename T> struct IntField {
     __device__ __forceinline__ static T fwd_word(Elem v, const Ctx &c) { return csub(csub(v, c.two_q), c.q); }
     __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return fwd_word(v, c); }
     __device__ __forceinline__ static T inv_word(Elem v, const Ctx &) { return v; }
+    __device__ __forceinline__ static Elem inv_bits(Elem v, const Ctx &) { return v; }
     // forward outputs a, b -> a*b mod q as an inverse-transform input (BarrettModulus::reduce_mul)
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return barrett_mul<T>(c.br, fwd_word(a, c), fwd_word(b, c)); }
     // key-MAC results (canonical words here) as inverse-transform inputs / as canonical output bits
@@ -293,6 +294,7 @@ struct F64Field {
     __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) {  // v in (-q, q)
         return csub<uint64_t>(mant(__dadd_rn(v, c.off1)), c.qi);
     }
+    __device__ __forceinline__ static Elem inv_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)inv_word(v, c)); }
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) { return mulmod(fold(a, c), fold(b, c), c); }
     // key-MAC results (doubles in (-q, q)) as inverse-transform inputs / as canonical output bits
     __device__ __forceinline__ static Elem from_mac(double v, const Ctx &) { return v; }
@@ -367,6 +369,7 @@ struct F64LazyField : F64Field {
     __device__ __forceinline__ static uint64_t fwd_word(Elem v, const Ctx &c) { return canon(v, c); }
     __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
     __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) { return canon(v, c); }
+    __device__ __forceinline__ static Elem inv_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
     // forward outputs (|a|,|b| < 7.76 q) -> centred product, ready for the first inverse pass
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) {
         refold(b, c);
