@@ -107,14 +107,15 @@ struct IoMaps {
     CUtensorMap in, out;
     const void *src;  // forward input (plain pointer: the forward transform reads with LDG)
 };
-template <typename T, int E> constexpr bool tma_row() { return sizeof(T) * E == 128; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// elected thread: shared (swizzled) -> global tensor rows [row, row + N/E); returns once shared memory has been read
-__device__ __forceinline__ void tma_store_poly(const CUtensorMap *map, const void *sm, uint32_t row) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0u), "r"(row), "r"(smem_addr(sm))
-                 : "memory");
+// elected thread: shared (swizzled) -> global tensor rows [row, row + boxes*box_rows); returns once shared memory has been read
+__device__ __forceinline__ void tma_store_poly(const CUtensorMap *map, const void *sm, uint32_t row, int boxes, int box_rows) {
+    for (int bx = 0; bx < boxes; bx++)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0u), "r"(row + bx * box_rows),
+                     "r"(smem_addr(sm) + (uint32_t)bx * box_rows * 128u)
+                     : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
@@ -123,11 +124,13 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 // elected thread: global tensor rows -> shared (swizzled), completion on the mbarrier
-__device__ __forceinline__ void tma_load_poly(const CUtensorMap *map, void *sm, uint32_t row, uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(sm)),
-                 "l"(map), "r"(0u), "r"(row), "r"(smem_addr(bar))
-                 : "memory");
+__device__ __forceinline__ void tma_load_poly(const CUtensorMap *map, void *sm, uint32_t row, uint64_t *bar, int boxes, int box_rows) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((uint32_t)(boxes * box_rows) * 128u) : "memory");
+    for (int bx = 0; bx < boxes; bx++)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                         smem_addr(sm) + (uint32_t)bx * box_rows * 128u),
+                     "l"(map), "r"(0u), "r"(row + bx * box_rows), "r"(smem_addr(bar))
+                     : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -219,11 +222,11 @@ template <typename F, int LOGN, int LOGE, int PPB, bool FWD, bool MULTI>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ntt_min_blocks<F, LOGN, LOGE, PPB>())
 ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
                size_t npolys, const __grid_constant__ IoMaps maps) {
-    using Core = NttCore<F, LOGN, LOGE>;
+    using Core = NttCore<F, LOGN, LOGE, true>;
     using T = typename F::WordT;
     using Elem = typename F::Elem;
     constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
-    static_assert(tma_row<T, E>(), "TMA path needs 128-byte exchange-buffer rows");
+    static_assert(Core::kTmaSwizzle, "tensor copies need the SWIZZLE_128B-compatible exchange-buffer swizzle");
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     const int grp = threadIdx.x / TPP, t = threadIdx.x % TPP;
     Elem *sm = reinterpret_cast<Elem *>(smem_tma) + (size_t)grp * N;
@@ -237,7 +240,7 @@ ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     if (MULTI) tb_limb = tables[poly % (size_t)limbs];
     const DevNtt<T> &tb = MULTI ? tb_limb : tb0;
     const typename F::Ctx c = F::ctx(tb);
-    const uint32_t row = (uint32_t)(poly * (N / E));
+    const uint32_t row = (uint32_t)(poly * Core::kTmaRows);
     typename SyncFor<TPP>::type sync;
     Elem x[E];
     if (FWD) {
@@ -248,7 +251,7 @@ ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
         uint64_t *bar = reinterpret_cast<uint64_t *>(smem_tma + sizeof(T) * PPB * N) + grp;
         if (t == 0) {
             mbar_init(bar, 1);
-            tma_load_poly(&maps.in, sm, row, bar, (uint32_t)(sizeof(T) * N));
+            tma_load_poly(&maps.in, sm, row, bar, Core::kTmaBoxes, Core::kTmaBoxRows);
         }
         sync();  // barrier initialised before anyone polls it
         mbar_wait(bar, 0);
@@ -263,7 +266,7 @@ ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     }
     fence_async_smem();
     sync();
-    if (active && t == 0) tma_store_poly(&maps.out, sm, row);
+    if (active && t == 0) tma_store_poly(&maps.out, sm, row, Core::kTmaBoxes, Core::kTmaBoxRows);
 }
 
 template <typename F, int LOGN, int LOGE, int PPB, bool MULTI>
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, polymul_min_blocks
 polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
                    const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, size_t npolys,
                    const __grid_constant__ CUtensorMap out_map) {
-    using Core = NttCore<F, LOGN, LOGE>;
+    using Core = NttCore<F, LOGN, LOGE, true>;
     using T = typename F::WordT;
     using Elem = typename F::Elem;
     constexpr int TPP = Core::TPP, N = Core::N, E = Core::E;
@@ -301,7 +304,7 @@ polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const 
     if (active) Core::template sm_store<0>(xa, sm, t);
     fence_async_smem();
     sync();
-    if (active && t == 0) tma_store_poly(&out_map, sm, (uint32_t)(poly * (N / E)));
+    if (active && t == 0) tma_store_poly(&out_map, sm, (uint32_t)(poly * Core::kTmaRows), Core::kTmaBoxes, Core::kTmaBoxRows);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -449,15 +452,15 @@ static TensorMapEncodeFn tensor_map_encoder() {
 }
 
 
-// tensor map over a batch of polynomials viewed as rows of E words: {E, npolys * N/E}, box {E, N/E}, SWIZZLE_128B
-template <typename T> static bool make_poly_map(CUtensorMap *map, const T *base, size_t npolys, int log_n, int log_e) {
+// tensor map over a batch of polynomials viewed as 128-byte rows: {128/w, npolys * N*w/128}, box {128/w, min(rows, 256)}, SWIZZLE_128B
+template <typename T> static bool make_poly_map(CUtensorMap *map, const T *base, size_t npolys, int log_n) {
     TensorMapEncodeFn enc = tensor_map_encoder();
-    const uint64_t rows = (uint64_t)1 << (log_n - log_e), total_rows = (uint64_t)npolys * rows;
-    const uint64_t e = (uint64_t)1 << log_e;
-    if (!enc || total_rows > 0xffffffffull || rows > 256 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const uint64_t e = 128 / sizeof(T);  // words per 128-byte row
+    const uint64_t rows = ((uint64_t)1 << log_n) / e, total_rows = (uint64_t)npolys * rows;
+    if (!enc || total_rows > 0xffffffffull || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)e, (cuuint64_t)total_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)(e * sizeof(T))};
-    const cuuint32_t box[2] = {(cuuint32_t)e, (cuuint32_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)128};
+    const cuuint32_t box[2] = {(cuuint32_t)e, (cuuint32_t)(rows < 256 ? rows : 256)};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<T *>(base), gdim, gstride, box,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -472,11 +475,14 @@ static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
     cudaError_t e;
-    if constexpr (tma_row<T, (1 << LOGE)>() && (1 << (LOGN - LOGE)) <= 256) {
+    // tensor copies: every direction where a thread row is 128 bytes; forward only for 256-byte rows (measured: +4..9 %
+    // forward, but the 2-way conflicted row pattern costs the inverse and the fused product more than the copy-out saves)
+    constexpr bool kRow128 = sizeof(T) * (1 << LOGE) == 128;
+    {
         static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;  // A/B tuning hook
         IoMaps maps;
         maps.src = src;
-        if (use_tma && make_poly_map<T>(&maps.out, dst, npolys, LOGN, LOGE) && (fwd || make_poly_map<T>(&maps.in, src, npolys, LOGN, LOGE))) {
+        if (use_tma && (kRow128 || fwd) && make_poly_map<T>(&maps.out, dst, npolys, LOGN) && (fwd || make_poly_map<T>(&maps.in, src, npolys, LOGN))) {
             if (fwd) memset(&maps.in, 0, sizeof(maps.in));
             auto launch = [&](auto k, size_t bytes) -> cudaError_t {
                 if (bytes > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
@@ -517,10 +523,10 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
     cudaError_t e;
-    if constexpr (tma_row<T, (1 << LOGE)>() && (1 << (LOGN - LOGE)) <= 256) {
+    if constexpr (sizeof(T) * (1 << LOGE) == 128) {
         static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;
         CUtensorMap map;
-        if (use_tma && make_poly_map<T>(&map, c, npolys, LOGN, LOGE)) {
+        if (use_tma && make_poly_map<T>(&map, c, npolys, LOGN)) {
             auto launch = [&](auto k) -> cudaError_t {
                 if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
                 k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, npolys, map);

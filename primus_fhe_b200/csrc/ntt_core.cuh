@@ -379,7 +379,7 @@ struct F64LazyField : F64Field {
     }
 };
 
-template <typename F, int LOGN, int LOGE> struct NttCore {
+template <typename F, int LOGN, int LOGE, bool TMA_SWZ = false> struct NttCore {
     using P = Plan<LOGN, LOGE>;
     using T = typename F::WordT;   // word type in global memory
     using Elem = typename F::Elem; // register / shared-memory representation
@@ -389,7 +389,17 @@ template <typename F, int LOGN, int LOGE> struct NttCore {
     static constexpr int N = P::N, E = P::E, TPP = P::TPP;
     static constexpr int CW = 16 / sizeof(T);                // words per 16-byte chunk
     static constexpr int SW_DST = (sizeof(T) == 8) ? 1 : 2;  // log2(CW)
-    static constexpr int SW_ROW = (LOGE - SW_DST) > 3 ? (LOGE - SW_DST) : 3;
+    // XOR source: bits 7..9 of the byte address is exactly TMA's SWIZZLE_128B, so a tensor copy can move whole polynomials
+    // between the swizzled buffer and linear HBM.  For thread rows of 128 bytes or less this is also the conflict-free
+    // choice.  For 256-byte rows (u64 E = 32, u32 E = 64) the conflict-free source is one bit higher; TMA_SWZ = true
+    // selects the TMA-compatible one anyway (2-way conflicts on the contiguous-per-thread pattern) -- worth it only for
+    // the forward transform, whose copy-out it replaces (measured).
+    static constexpr int SW_ROW = (TMA_SWZ || (LOGE - SW_DST) <= 3) ? 3 : (LOGE - SW_DST);
+    static constexpr bool kTmaSwizzle = SW_ROW == 3;
+    static constexpr int kRowWords = 128 / (int)sizeof(T);                     // one TMA row = 128 bytes
+    static constexpr int kTmaRows = N / kRowWords;                             // rows per polynomial
+    static constexpr int kTmaBoxRows = kTmaRows < 256 ? kTmaRows : 256;        // box height limit of a tensor map
+    static constexpr int kTmaBoxes = kTmaRows / kTmaBoxRows;
     static constexpr int SW_SRC = SW_DST + SW_ROW;
     static constexpr int NV = E / CW > 0 ? E / CW : 1;       // 16-byte vectors per thread row
     static_assert(E >= CW, "a thread row must hold at least one 16-byte chunk");
