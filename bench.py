@@ -75,6 +75,36 @@ def _c3_primes():
     return out
 
 
+def _bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process (and therefore the first-touch placement of its pinned host buffers) to the NUMA node the GPU
+    hangs off: the e2e path moves 4 GiB per step over PCIe, cross-socket traffic halves it at 8 ranks."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = gpu_index
+        if vis and all(p.strip().isdigit() for p in vis.split(",")):
+            idx = int(vis.split(",")[gpu_index])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -210,10 +240,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = _bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
+    # stdout carries exactly ONE JSON line: anything libraries print at the C level (NCCL's version banner ...) is sent to
+    # stderr by swapping the descriptors for the duration of the run; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version/debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -367,9 +401,11 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_batch * N * 8, "d2h_bytes_per_step": e2e_batch * N * 8,
                     "api": "pfhe_ntt64_transform_slices (host-slice shim of NttTable::transform_slice, pinned host memory)",
+                    "numa_node_rank0": numa_node,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
     return 0
