@@ -1,0 +1,84 @@
+"""Every tuning hook selects a different kernel for the same mathematical function: all of them must give the same bits.
+(PFHE_NTT_TMA=0 -> LSU copy-out/copy-in kernels; PFHE_F64_LAZY=0 -> per-stage-fold FP64 butterflies; PFHE_DISABLE_F64=1 ->
+integer-pipe butterflies; PFHE_DISABLE_WIDE32=1 -> Harvey forward butterflies in the lattice kernels.)  The hooks are read once
+per process, so each setting runs in a subprocess that prints digests of its outputs; the default setting is additionally
+checked against the CPU oracle in the other test modules."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import sys, json, hashlib
+sys.path.insert(0, %r)
+import numpy as np, torch
+import primus_fhe_b200 as P
+out = {}
+def dig(t): return hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()
+rng = np.random.default_rng(123)
+for bits, log_n, q, batch in [(64, 12, 1125899906826241, 5), (64, 11, 1125899906826241, 7), (64, 13, 1125899906826241, 3),
+                              (64, 10, 1125899906826241, 9), (32, 10, 132120577, 9), (32, 12, 268369921, 3), (32, 13, 132120577, 2)]:
+    n = 1 << log_n
+    t = (P.U64NttTable if bits == 64 else P.U32NttTable)(log_n, q)
+    x = rng.integers(0, q, (batch, n), dtype=np.uint64)
+    x[0, :] = q - 1; x[-1, :] = 0
+    tdt = torch.int64 if bits == 64 else torch.int32
+    d = torch.from_numpy(x.astype(np.int64)).to(tdt).cuda()
+    e = d.flip(0).contiguous()
+    key = f"u{bits}_n{n}"
+    f = d.clone(); t.forward_batch(f); out[key + "_fwd"] = dig(f)
+    g = torch.empty_like(d); t.forward_batch_to(d, g); assert torch.equal(f, g)
+    i = d.clone(); t.inverse_batch(i); out[key + "_inv"] = dig(i)
+    c = torch.empty_like(d); t.polymul_batch(d, e, c); out[key + "_mul"] = dig(c)
+# DCRT (per-limb tables) through the same kernels
+mods = [1125899906826241, 1125899906629633, 1125899904679937]
+dc = P.U64DcrtTable(12, mods)
+x = np.stack([rng.integers(0, m, (3, 4096), dtype=np.uint64) for m in mods], axis=1)
+d = torch.from_numpy(x.astype(np.int64)).cuda().contiguous()
+f = d.clone(); dc.forward_batch(f); out["dcrt_fwd"] = dig(f)
+i = d.clone(); dc.inverse_batch(i); out["dcrt_inv"] = dig(i)
+c = torch.empty_like(d); dc.polymul_batch(d, d.flip(0).contiguous(), c); out["dcrt_mul"] = dig(c)
+# lattice kernels (u32 wide forward / Harvey forward, u64 FP64 / integer)
+for bits, q in ((32, 132120577), (64, 1125899906826241)):
+    t = (P.U64NttTable if bits == 64 else P.U32NttTable)(10, q)
+    lv = P.ApproxSignedBasis(q, 7, None, bits).decompose_length()
+    tdt = torch.int64 if bits == 64 else torch.int32
+    key_ = torch.from_numpy(rng.integers(0, q, 2 * lv * 2 * 1024, dtype=np.uint64).astype(np.int64)).to(tdt).cuda()
+    cin = torch.from_numpy(rng.integers(0, q, (4, 2048), dtype=np.uint64).astype(np.int64)).to(tdt).cuda()
+    o = torch.empty_like(cin); t.external_product_batch(1, 7, None, key_, cin, o, True); out[f"ep{bits}"] = dig(o)
+print("DIGESTS " + json.dumps(out))
+''' % ROOT
+
+
+def _run(env):
+    p = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("DIGESTS ")]
+    assert lines, p.stderr[-3000:]
+    return json.loads(lines[0][8:])
+
+
+def test_all_kernel_variants_agree_bit_for_bit():
+    base = _run({})
+    for env in ({"PFHE_NTT_TMA": "0"}, {"PFHE_F64_LAZY": "0"}, {"PFHE_DISABLE_F64": "1"}, {"PFHE_DISABLE_WIDE32": "1"},
+                {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}):
+        other = _run(env)
+        diff = [k for k in base if base[k] != other[k]]
+        assert not diff, (env, diff)
+
+
+def test_empty_batches_are_noops():
+    import torch
+    import primus_fhe_b200 as P
+    t = P.U64NttTable(12, 1125899906826241)
+    e = torch.empty((0, 4096), dtype=torch.int64, device="cuda")
+    t.forward_batch(e); t.inverse_batch(e); t.polymul_batch(e, e, e)
+    dc = P.U64DcrtTable(10, [1125899906826241, 1125899906629633])
+    e2 = torch.empty((0, 2, 1024), dtype=torch.int64, device="cuda")
+    dc.forward_batch(e2); dc.inverse_batch(e2)
+    torch.cuda.synchronize()
