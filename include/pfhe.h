@@ -208,6 +208,20 @@ pfhe_status pfhe_mod64_slice_op(pfhe_slice_op op, const uint64_t *moduli, size_t
 pfhe_status pfhe_mod32_slice_op(pfhe_slice_op op, const uint32_t *moduli, size_t limbs, const uint32_t *scalars,
                                 const uint32_t *a, const uint32_t *b, const uint32_t *c, uint32_t *out,
                                 size_t rows, size_t n, void *stream);
+/* DcrtPolynomial::butterfly_mul_factor_to / DcrtGlwe::butterfly_mul_factor_to (primus_poly/src/dcrt/mul.rs:189-222,
+ * primus_lattice/src/glwe/dcrt.rs:150-175): (a, out) = (a + s, (a_orig - s) * w) per limb; a, s, out: device [rows][limbs][n]
+ * in [0,q), a updated in place; w: device [limbs][n] factor polynomial (values; the Shoup quotients of the reference's
+ * ShoupFactor array are not needed, the product is the same residue). */
+pfhe_status pfhe_mod64_butterfly_mul_factor(const uint64_t *moduli, size_t limbs, uint64_t *a, const uint64_t *s, const uint64_t *w,
+                                            uint64_t *out, size_t rows, size_t n, void *stream);
+pfhe_status pfhe_mod32_butterfly_mul_factor(const uint32_t *moduli, size_t limbs, uint32_t *a, const uint32_t *s, const uint32_t *w,
+                                            uint32_t *out, size_t rows, size_t n, void *stream);
+/* ReduceInvSlice::reduce_inv_slice_to / NttPolynomial::inv_to (primus_poly/src/ntt/inv.rs:1-58, primus_reduce/src/slice_ops.rs:255-300):
+ * out[i] = a[i]^-1 mod q for a PRIME q (every NTT modulus is).  Zero has no inverse: out[i] = 0 and, when `first_bad` (device
+ * uint64, initialised by the caller to ~0) is not NULL, the smallest such index is recorded -- try_reduce_inv_slice_to's
+ * ReduceError::NoInverseAtIndex (primus_reduce/src/error.rs:23). */
+pfhe_status pfhe_mod64_inv_slice(uint64_t q, const uint64_t *a, uint64_t *out, size_t count, uint64_t *first_bad, void *stream);
+pfhe_status pfhe_mod32_inv_slice(uint32_t q, const uint32_t *a, uint32_t *out, size_t count, uint64_t *first_bad, void *stream);
 /* Host-slice shims of the same operators (HOST pointers; H2D -> kernel -> D2H). */
 pfhe_status pfhe_mod64_slice_op_host(pfhe_slice_op op, const uint64_t *moduli, size_t limbs, const uint64_t *scalars,
                                      const uint64_t *a, const uint64_t *b, const uint64_t *c, uint64_t *out,

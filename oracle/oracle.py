@@ -544,6 +544,20 @@ class BigUintApproxSignedBasis:
         f(self._h, level, _ptr(big_values), _ptr(dig), _ptr(carries), n); return dig
 
 
+
+def butterfly_mul_factor(a, s, w, moduli, n):
+    """DcrtPolynomial::butterfly_mul_factor_to (primus_poly/src/dcrt/mul.rs:189-222; scalar body slice_butterfly):
+    (a, out) = (a + s, (a - s) * w) mod q per limb.  a, s: [rows][L][n]; w: [L][n].  Exact big-int restatement."""
+    a = np.asarray(a); s_ = np.asarray(s); w = np.asarray(w)
+    L = len(moduli)
+    A = a.reshape(-1, L, n).astype(object); S = s_.reshape(-1, L, n).astype(object); W = w.reshape(L, n).astype(object)
+    new_a = np.empty_like(A); out = np.empty_like(A)
+    for li, q in enumerate(moduli):
+        new_a[:, li, :] = (A[:, li, :] + S[:, li, :]) % q
+        out[:, li, :] = ((A[:, li, :] - S[:, li, :]) % q) * W[li][None, :] % q
+    return new_a.astype(a.dtype).reshape(a.shape), out.astype(a.dtype).reshape(a.shape)
+
+
 # --------------------------------------------------------------------------- products
 class DcrtTable:
     """One table per limb, looped (primus_ntt/src/dcrt/prime64.rs:11-128)."""

@@ -546,6 +546,28 @@ def mul_monomial_batch(moduli, degrees, polys, out, log_n, bits=64):
     check(f(m, L, _dev_ptr(degrees, 32, batch), _dev_ptr(polys, bits), _dev_ptr(out, bits, polys.numel()), log_n, batch, _stream()))
 
 
+def butterfly_mul_factor_batch(moduli, a, s, w, out, n, bits=64):
+    """(a, out) = (a + s, (a - s) * w) per limb (primus_poly/src/dcrt/mul.rs:189-222). a, s, out: CUDA [rows][L][n]; w: CUDA [L][n]."""
+    L = len(moduli)
+    m = (_ct(bits) * L)(*[int(x) for x in moduli])
+    rows = a.numel() // (L * n)
+    f = getattr(lib(), f"pfhe_mod{bits}_butterfly_mul_factor")
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    check(f(m, L, _dev_ptr(a, bits), _dev_ptr(s, bits, a.numel()), _dev_ptr(w, bits, L * n), _dev_ptr(out, bits, a.numel()), rows, n, _stream()))
+
+
+def inv_slice_batch(q, a, out, bits=64):
+    """out = a^-1 mod q element-wise (prime q). Returns the smallest index without an inverse (zero element) or None
+    (try_reduce_inv_slice_to, primus_reduce/src/slice_ops.rs:293-300)."""
+    import torch
+    bad = torch.full((1,), -1, dtype=torch.int64, device=a.device)
+    f = getattr(lib(), f"pfhe_mod{bits}_inv_slice")
+    f.argtypes = [_ct(bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    check(f(int(q), _dev_ptr(a, bits), _dev_ptr(out, bits, a.numel()), a.numel(), C.c_void_p(bad.data_ptr()), _stream()))
+    v = int(bad.item())
+    return None if v == -1 else v
+
+
 def dot_product_batch(q, a, b, out, n, bits=64):
     """reduce_dot_product per row (primus_modulus/src/common/compact/slice.rs:371-438). a, b: CUDA [rows][n]; out: CUDA [rows]."""
     rows = a.numel() // n

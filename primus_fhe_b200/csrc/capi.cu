@@ -730,6 +730,24 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
                                             const T *b, const T *c, T *out, size_t rows, size_t n) {                                  \
         return slice_op_host<T>((int)op, moduli, limbs, scalars, a, b, c, out, rows, n);                                              \
     }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_butterfly_mul_factor(const T *moduli, size_t limbs, T *a, const T *s, const T *w, T *out, size_t rows,    \
+                                                   size_t n, void *stream) {                                                          \
+        LimbConsts<T> lc;                                                                                                             \
+        pfhe_status st = make_limb_consts<T>(moduli, limbs, nullptr, PFHE_OP_MUL, lc);                                                \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if ((!a || !s || !w || !out) && rows * n) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_CUDA(launch_butterfly_mul<T>(lc, (int)limbs, a, s, w, out, rows, n, static_cast<cudaStream_t>(stream)));                 \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_inv_slice(T q, const T *a, T *out, size_t count, uint64_t *first_bad, void *stream) {                   \
+        LimbConsts<T> lc;                                                                                                             \
+        pfhe_status st = make_limb_consts<T>(&q, 1, nullptr, PFHE_OP_MUL, lc);                                                        \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        if ((!a || !out) && count) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_CUDA(launch_inv_slice<T>(lc.br[0], a, out, count, reinterpret_cast<unsigned long long *>(first_bad),                     \
+                                      static_cast<cudaStream_t>(stream)));                                                            \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
     pfhe_status pfhe_basis##B##_geometry(T q, uint32_t log_basis, uint32_t levels_in, uint32_t *levels, uint32_t *drop_bits) {        \
         GadgetParams<T> g;                                                                                                            \
         if (!make_gadget<T>(q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;                                                 \

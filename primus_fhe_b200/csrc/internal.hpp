@@ -51,6 +51,11 @@ template <typename T>
 cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out,
                             size_t rows, size_t n, cudaStream_t stream);
 template <typename T>
+cudaError_t launch_butterfly_mul(const LimbConsts<T> &lc, int limbs, T *a, const T *s, const T *w, T *out, size_t rows, size_t n,
+                                 cudaStream_t stream);
+template <typename T>
+cudaError_t launch_inv_slice(const Barrett<T> &br, const T *a, T *out, size_t count, unsigned long long *first_bad, cudaStream_t stream);
+template <typename T>
 cudaError_t launch_decompose(const GadgetParams<T> &g, const T *values, T *digits, size_t count, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_rns_lift(const T *moduli_host, int limbs, T small_modulus, const T *small, T *out, size_t count,

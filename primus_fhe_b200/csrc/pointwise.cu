@@ -102,6 +102,72 @@ static cudaError_t run_slice_op(const LimbConsts<T> &lc, int limbs, const T *a, 
     return cudaGetLastError();
 }
 
+// Inverse butterfly with a factor polynomial, per limb: (a, out) = (a + s, (a - s) * w)   (all in [0, q))
+// DcrtPolynomial::butterfly_mul_factor_to  primus_poly/src/dcrt/mul.rs:189-222 (DcrtGlwe form: primus_lattice/src/glwe/dcrt.rs:150-175).
+// The reference multiplies with a precomputed ShoupFactor array; the product is the same residue, computed here by Barrett.
+template <typename T>
+__global__ void __launch_bounds__(256) butterfly_mul_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, T *__restrict__ a,
+                                                            const T *__restrict__ s, const T *__restrict__ w, T *__restrict__ out, size_t rows,
+                                                            size_t n) {
+    const size_t total = rows * (size_t)limbs * n;
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+        const int limb = limbs == 1 ? 0 : (int)((gid / n) % (size_t)limbs);
+        const Barrett<T> br = lc.br[limb];
+        const T x = a[gid], y = s[gid];
+        // w is one factor polynomial per limb, shared by every row (factor_poly: [limbs][n])
+        const T f = w[(size_t)limb * n + gid % n];
+        a[gid] = mod_add<T>(x, y, br.q);
+        out[gid] = barrett_mul<T>(br, mod_sub<T>(x, y, br.q), f);
+    }
+}
+template <typename T>
+cudaError_t launch_butterfly_mul(const LimbConsts<T> &lc, int limbs, T *a, const T *s, const T *w, T *out, size_t rows, size_t n,
+                                 cudaStream_t stream) {
+    const size_t total = rows * (size_t)limbs * n;
+    if (!total) return cudaSuccess;
+    butterfly_mul_kernel<T><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, s, w, out, rows, n);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_butterfly_mul<uint32_t>(const LimbConsts<uint32_t> &, int, uint32_t *, const uint32_t *, const uint32_t *, uint32_t *,
+                                                    size_t, size_t, cudaStream_t);
+template cudaError_t launch_butterfly_mul<uint64_t>(const LimbConsts<uint64_t> &, int, uint64_t *, const uint64_t *, const uint64_t *, uint64_t *,
+                                                    size_t, size_t, cudaStream_t);
+
+// Element-wise modular inverse over a prime modulus (every NTT modulus is prime): a^(q-2) by square-and-multiply with
+// Barrett products.  Replaces ReduceInvSlice::reduce_inv_slice_to / NttPolynomial::inv_to (primus_poly/src/ntt/inv.rs:1-58;
+// the CPU uses Montgomery's batch-inversion trick, primus_modulus/src/barrett/slice.rs:499-625 -- a serial prefix product
+// that does not map to one-thread-per-element; the inverse is unique, so the results are the same bits).
+// Non-invertible (zero) inputs give 0 and, like try_reduce_inv_slice_to -> ReduceError::NoInverseAtIndex, report the
+// smallest offending index through *first_bad (atomicMin; initialise to ~0ull).
+template <typename T>
+__global__ void __launch_bounds__(256) inv_slice_kernel(const Barrett<T> br, const T *__restrict__ a, T *__restrict__ out, size_t count,
+                                                        unsigned long long *first_bad) {
+    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < count; gid += (size_t)gridDim.x * blockDim.x) {
+        const T x = a[gid];
+        T e = br.q - 2, base = x, r = 1;
+        while (e) {
+            if (e & 1) r = barrett_mul<T>(br, r, base);
+            base = barrett_mul<T>(br, base, base);
+            e >>= 1;
+        }
+        if (x == 0) {
+            r = 0;
+            if (first_bad) atomicMin(first_bad, (unsigned long long)gid);
+        }
+        out[gid] = r;
+    }
+}
+template <typename T>
+cudaError_t launch_inv_slice(const Barrett<T> &br, const T *a, T *out, size_t count, unsigned long long *first_bad, cudaStream_t stream) {
+    if (!count) return cudaSuccess;
+    inv_slice_kernel<T><<<stream_grid(count, 256), 256, 0, stream>>>(br, a, out, count, first_bad);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_inv_slice<uint32_t>(const Barrett<uint32_t> &, const uint32_t *, uint32_t *, size_t, unsigned long long *, cudaStream_t);
+template cudaError_t launch_inv_slice<uint64_t>(const Barrett<uint64_t> &, const uint64_t *, uint64_t *, size_t, unsigned long long *, cudaStream_t);
+
 template <typename T>
 cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out, size_t rows, size_t n,
                             cudaStream_t s) {

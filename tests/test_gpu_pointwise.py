@@ -136,3 +136,44 @@ def test_rns_lift_and_extract_lwe():
     got = _host(out, np.uint32)
     for i in range(batch):
         assert np.array_equal(got[i], O.extract_lwe(rl[i], Q27, 32))
+
+
+@pytest.mark.parametrize("bits,moduli,n", [(64, [1125899906826241], 1024), (64, [1125899906826241, 1125899906629633, 562949953392641], 256),
+                                           (32, [132120577, 134176769], 2048), (64, [1152921504606830593], 7)])
+def test_butterfly_mul_factor_matches_oracle(bits, moduli, n):
+    """(a, out) = (a + s, (a - s) * w): DcrtPolynomial::butterfly_mul_factor_to (primus_poly/src/dcrt/mul.rs:189-222)."""
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(6)
+    rows, L = 3, len(moduli)
+    mk = lambda r: np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64).astype(dt) for m in moduli]) for _ in range(r)])
+    a, s, w = mk(rows), mk(rows), mk(1)[0]
+    a[0, :, 0] = 0; s[0, :, 0] = np.array([m - 1 for m in moduli], dtype=dt)
+    want_a, want_out = O.butterfly_mul_factor(a, s, w, moduli, n)
+    da, ds, dw = _dev(a.copy()), _dev(s), _dev(w)
+    out = torch.empty_like(da)
+    P.butterfly_mul_factor_batch(moduli, da, ds, dw, out, n, bits)
+    assert np.array_equal(da.cpu().numpy().view(dt).reshape(a.shape), want_a)
+    assert np.array_equal(out.cpu().numpy().view(dt).reshape(a.shape), want_out)
+
+
+@pytest.mark.parametrize("bits,q", [(64, 1125899906826241), (64, 1152921504606830593), (32, 132120577), (32, 1073692673)])
+def test_inv_slice_matches_bigint(bits, q):
+    """NttPolynomial::inv_to / reduce_inv_slice_to (primus_poly/src/ntt/inv.rs:1-58): the modular inverse is unique, so the
+    check is exact big-int arithmetic (pow(a, -1, q)) plus a * a^-1 == 1 through the GPU's own product."""
+    import torch
+    import primus_fhe_b200 as P
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(3)
+    n = 500
+    a = rng.integers(1, q, n, dtype=np.uint64).astype(dt)
+    a[0], a[1] = 1, q - 1
+    da = _dev(a); out = torch.empty_like(da)
+    assert P.inv_slice_batch(q, da, out, bits) is None
+    got = out.cpu().numpy().view(dt)
+    assert [int(v) for v in got] == [pow(int(v), -1, q) for v in a]
+    a[7] = 0; a[300] = 0                                   # try_reduce_inv_slice_to -> NoInverseAtIndex { index: 7 }
+    assert P.inv_slice_batch(q, _dev(a), out, bits) == 7
+    assert int(out.cpu().numpy().view(dt)[7]) == 0
