@@ -325,7 +325,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "ntt_kernel<u64,N=4096> forward", "algorithmic_bytes_per_launch": batch * BYTES_PER_NTT,
+                "peak_source": peak_src, "kernel": "ntt_tma_kernel<F64LazyField,N=4096> forward (lazy-fold FP64 butterflies, TMA tensor store)", "algorithmic_bytes_per_launch": batch * BYTES_PER_NTT,
                 "avg_launch_ms": avg_kernel_ms,
                 "modmul": {"butterflies_per_s": batch * MODMULS_PER_NTT / (avg_kernel_ms * 1e-3),
                            "fp64_instr_per_ntt": FP64_PER_NTT, "fp64_pipe_peak_instr_per_s": FP64_PEAK,
