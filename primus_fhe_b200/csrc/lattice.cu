@@ -52,6 +52,7 @@ template <> struct LatAcc<IntField<uint32_t>> {
     using F = IntField<uint32_t>;
     using Acc = uint64_t;
     static constexpr bool kRenorm = true;
+    static constexpr uint32_t kRenormEvery = 16;
     __device__ __forceinline__ static void zero(Acc &a) { a = 0; }
     __device__ __forceinline__ static uint32_t prepare(uint32_t x, const F::Ctx &c) { return F::fwd_word(x, c); }
     __device__ __forceinline__ static void mac(Acc &a, uint32_t x, uint32_t key, const F::Ctx &) { mac_wide(a, x, key); }
@@ -67,6 +68,7 @@ template <> struct LatAcc<IntField<uint64_t>> {
     using F = IntField<uint64_t>;
     using Acc = Wide2<uint64_t>;
     static constexpr bool kRenorm = true;
+    static constexpr uint32_t kRenormEvery = 16;
     __device__ __forceinline__ static void zero(Acc &a) { a.lo = 0; a.hi = 0; }
     __device__ __forceinline__ static uint64_t prepare(uint64_t x, const F::Ctx &c) { return F::fwd_word(x, c); }
     __device__ __forceinline__ static void mac(Acc &a, uint64_t x, uint64_t key, const F::Ctx &) { mac_wide(a, x, key); }
@@ -77,6 +79,7 @@ template <> struct LatAcc<F64Field> {
     using F = F64Field;
     using Acc = double;
     static constexpr bool kRenorm = false;
+    static constexpr uint32_t kRenormEvery = 16;
     __device__ __forceinline__ static void zero(Acc &a) { a = 0.0; }
     __device__ __forceinline__ static double prepare(double x, const F::Ctx &) { return x; }  // |x| < 2q is a valid multiplier input
     __device__ __forceinline__ static void mac(Acc &a, double x, uint64_t key, const F::Ctx &c) {
@@ -84,6 +87,30 @@ template <> struct LatAcc<F64Field> {
     }
     __device__ __forceinline__ static void renorm(Acc &, const F::Ctx &) {}
     __device__ __forceinline__ static double final(const Acc &a, const F::Ctx &) { return a; }  // (-q, q): inverse-transform input
+};
+
+// FP64 pipe, lazy folds (F64LazyField): the transformed digit is folded once to |x| <= q/2 + 1, every product is then
+// below 0.625 q in magnitude (level-0 quotient), and the accumulator is folded after 8 terms (8 * 0.625 q + q/2 < 8 q <= 2^53,
+// all sums exact).  No per-term fold, no integer-ALU work.
+template <> struct LatAcc<F64LazyField> {
+    using F = F64LazyField;
+    using Acc = double;
+    static constexpr bool kRenorm = true;
+    static constexpr uint32_t kRenormEvery = 8;
+    __device__ __forceinline__ static void zero(Acc &a) { a = 0.0; }
+    __device__ __forceinline__ static double prepare(double x, const F::Ctx &c) {
+        F::refold(x, c);
+        return x;
+    }
+    __device__ __forceinline__ static void mac(Acc &a, double x, uint64_t key, const F::Ctx &c) {
+        a = __dadd_rn(a, F::mulmod(x, F::from_u64(key), c, 0));
+    }
+    __device__ __forceinline__ static void renorm(Acc &a, const F::Ctx &c) { F::refold(a, c); }
+    __device__ __forceinline__ static double final(const Acc &a, const F::Ctx &c) {  // centred: first inverse pass input
+        double v = a;
+        F::refold(v, c);
+        return v;
+    }
 };
 
 // init_value_carry (primus_decompose/src/primitive/basis.rs:254-283): adjusted value + initial carry
@@ -140,7 +167,7 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
                 const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
                 if (LA::kRenorm) {
-                    if (terms == 16) {  // keep the lazy double-word sums below 2^(2*BITS)
+                    if (terms == LA::kRenormEvery) {  // keep the lazy sums inside their exact range
 #pragma unroll
                         for (int c = 0; c < COMPS; c++)
 #pragma unroll
@@ -342,6 +369,8 @@ template <typename T, int LOGN, int LOGE, int COMPS, int PPB>
 static cudaError_t run_ep(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
                           cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
+        static const bool lazy = !(getenv("PFHE_F64_LAZY") && getenv("PFHE_F64_LAZY")[0] == '0');  // A/B tuning hook
+        if (tb.use_f64 && lazy) return run_ep_f<F64LazyField, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
         if (tb.use_f64) return run_ep_f<F64Field, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
     } else {
         if (wide32_ok(tb.q, LOGN)) return run_ep_f<IntWide32Field, LOGN, LOGE, COMPS, PPB>(tb, g, key, in, out, batch, to_coeff, stream);
@@ -352,6 +381,8 @@ template <typename T, int LOGN, int LOGE, int PPB, int MINB = 1>
 static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe, const uint32_t *lwe, const T *tv,
                           T *acc_out, size_t batch, cudaStream_t stream) {
     if constexpr (sizeof(T) == 8) {
+        static const bool lazy = !(getenv("PFHE_F64_LAZY") && getenv("PFHE_F64_LAZY")[0] == '0');
+        if (tb.use_f64 && lazy) return run_br_f<F64LazyField, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
         if (tb.use_f64) return run_br_f<F64Field, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
     } else {
         if (wide32_ok(tb.q, LOGN)) return run_br_f<IntWide32Field, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);

@@ -370,6 +370,9 @@ struct F64LazyField : F64Field {
     __device__ __forceinline__ static Elem fwd_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
     __device__ __forceinline__ static uint64_t inv_word(Elem v, const Ctx &c) { return canon(v, c); }
     __device__ __forceinline__ static Elem inv_bits(Elem v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
+    // key-MAC results (centred doubles) as inverse-transform inputs / as canonical output bits
+    __device__ __forceinline__ static Elem from_mac(double v, const Ctx &) { return v; }
+    __device__ __forceinline__ static Elem mac_bits(double v, const Ctx &c) { return __longlong_as_double((long long)canon(v, c)); }
     // forward outputs (|a|,|b| < 7.76 q) -> centred product, ready for the first inverse pass
     __device__ __forceinline__ static Elem pointwise(Elem a, Elem b, const Ctx &c) {
         refold(b, c);

@@ -75,6 +75,17 @@ def inverse(stages_per_pass, q):
     return float(worst / q)
 
 
+def mac_budget(q, every=8):
+    """Lattice key multiply-accumulate (LatAcc<F64LazyField>): digit folded to q/2+1, products at level 0, the accumulator
+    folded after `every` terms (the first batch starts from 0, later ones from a folded accumulator counted as one term)."""
+    x = fold_bound(Fr(8) * q, q)                 # |transformed digit| after the fold
+    t = mul_bound(x, 0, q)                       # |x * key mod q| with key < q
+    first = every * t
+    later = fold_bound(first, q) + (every - 1) * t
+    assert first <= LIMIT and later <= LIMIT
+    return float(max(first, later) / q)
+
+
 def plan(logn, loge):
     npass = (logn + loge - 1) // loge
     first = logn - (npass - 1) * loge
@@ -88,6 +99,7 @@ def check_all():
             for loge in (3, 4, 5):
                 pl = plan(logn, loge)
                 res[(q, logn, loge)] = (forward(pl, Fr(q)), inverse(list(reversed(pl)), Fr(q)))
+        assert mac_budget(Fr(q)) < 8.0
     return res
 
 
