@@ -153,15 +153,23 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
         for (int r = 0; r < COMPS; r++) {
             // adjusted coefficients and carries of this component stay in registers across the levels
             T adj[E];
-            uint32_t carry[E];
+            uint32_t carries = 0;  // one carry bit per element (a register each would push the kernel into spills)
 #pragma unroll
-            for (int j = 0; j < E; j++) adj[j] = gadget_init<T>(g, get(r, Core::elem_index(FB0, t, j)), carry[j]);
+            for (int j = 0; j < E; j++) {
+                uint32_t cj;
+                adj[j] = gadget_init<T>(g, get(r, Core::elem_index(FB0, t, j)), cj);
+                carries |= cj << j;
+            }
 #pragma unroll 1
             for (uint32_t l = 0; l < g.levels; l++) {
                 Elem x[E];
                 const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
-                for (int j = 0; j < E; j++) x[j] = F::load(gadget_level<T>(g, adj[j], shift, carry[j]), cx);
+                for (int j = 0; j < E; j++) {
+                    uint32_t cj = (carries >> j) & 1u;
+                    x[j] = F::load(gadget_level<T>(g, adj[j], shift, cj), cx);
+                    carries = (carries & ~(1u << j)) | (cj << j);
+                }
                 Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);  // releases the exchange buffer for the next digit
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
