@@ -614,7 +614,7 @@ const char *pfhe_status_string(pfhe_status s) {
     return "Unknown";
 }
 const char *pfhe_last_cuda_error(void) { return t_last_cuda_error.c_str(); }
-const char *pfhe_version(void) { return "primus_fhe_b200 0.1.0 (abi 1)"; }
+const char *pfhe_version(void) { return "primus_fhe_b200 0.2.0 (abi 2)"; }
 const char *pfhe_compiled_arch(void) { return "sm_100a"; }
 uint64_t pfhe_launch_count(void) { return g_launches.load(); }
 
