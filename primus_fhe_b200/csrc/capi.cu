@@ -512,6 +512,7 @@ static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t
     GadgetParams<T> g;
     if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
     if (t->dev_lat.loge == 0 || k < 1 || k > 2) return PFHE_ERR_UNSUPPORTED;
+    DeviceGuard guard(t->device);
     PFHE_CUDA(launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
@@ -522,6 +523,7 @@ static pfhe_status blind_rot(const H *t, uint32_t log_basis, uint32_t levels_in,
     GadgetParams<T> g;
     if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
     if (t->dev_lat.loge == 0) return PFHE_ERR_UNSUPPORTED;
+    DeviceGuard guard(t->device);
     PFHE_CUDA(launch_blind_rotate<T>(t->dev_lat, g, bsk, n_lwe, lwe, tv, acc_out, batch, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
@@ -577,6 +579,7 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
     const size_t per_ct = comps * g.levels * L * n * sizeof(T);
     if (!scratch || scratch_bytes < per_ct) return PFHE_ERR_INVALID_ARG;
     const size_t chunk = scratch_bytes / per_ct;
+    DeviceGuard guard(t->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     T *digits = static_cast<T *>(scratch);
     const size_t glwe_len = comps * L * n;
@@ -648,32 +651,38 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_forward_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, true, static_cast<cudaStream_t>(stream)));                       \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_inverse_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, false, static_cast<cudaStream_t>(stream)));                      \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_forward_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
         if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, true, static_cast<cudaStream_t>(stream)));                       \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_inverse_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
         if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, false, static_cast<cudaStream_t>(stream)));                      \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_monomial_batch(const pfhe_ntt##B *t, T coeff, const uint32_t *degrees, T *out, size_t batch,            \
                                              void *stream) {                                                                          \
         if (!t || ((!degrees || !out) && batch) || coeff >= t->h.q) return PFHE_ERR_INVALID_ARG;                                      \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_monomial<T>(t->dev, coeff, degrees, out, batch, static_cast<cudaStream_t>(stream)));                         \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_polymul_batch(const pfhe_ntt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {         \
         if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_polymul<T>(t->dev, nullptr, 1, a, b, c, batch, static_cast<cudaStream_t>(stream)));                          \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -706,18 +715,21 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_forward_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), true,         \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_inverse_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), false,        \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_polymul_batch(const pfhe_dcrt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {       \
         if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
+        DeviceGuard guard(t->device);                                                                                                 \
         PFHE_CUDA(launch_polymul<T>(t->tb0, t->d_tables, (int)t->limbs.size(), a, b, c, batch * t->limbs.size(),            \
                                     static_cast<cudaStream_t>(stream)));                                                              \
         return PFHE_OK;                                                                                                               \
