@@ -20,7 +20,8 @@ def _dev(x):
 
 @pytest.mark.parametrize("bits,q,log_n,log_basis,rev,k", [
     (32, Q27, 11, 7, None, 1), (64, Q50, 11, 7, None, 1), (32, Q27, 10, 7, None, 1), (64, Q50, 10, 7, 3, 1),
-    (64, Q50, 12, 10, None, 1), (32, Q27, 10, 4, None, 2), (64, Q50, 10, 2, None, 1)])
+    (64, Q50, 12, 10, None, 1), (32, Q27, 10, 4, None, 2), (64, Q50, 10, 2, None, 1), (64, Q50, 10, 7, None, 2), (64, Q50, 11, 3, None, 1),
+    (64, 1152921504606830593, 10, 7, None, 1), (64, 562949953392641, 11, 7, None, 1), (32, 1073692673, 10, 7, None, 1)])
 @pytest.mark.parametrize("to_coeff", [True, False])
 def test_external_product_matches_oracle(bits, q, log_n, log_basis, rev, k, to_coeff):
     import torch
@@ -44,7 +45,8 @@ def test_external_product_matches_oracle(bits, q, log_n, log_basis, rev, k, to_c
     assert np.array_equal(out.cpu().numpy().view(dt), want)
 
 
-@pytest.mark.parametrize("bits,q,log_n,log_basis,n_lwe", [(32, Q27, 10, 7, 12), (64, Q50, 10, 7, 5), (32, Q27, 11, 7, 4)])
+@pytest.mark.parametrize("bits,q,log_n,log_basis,n_lwe", [(32, Q27, 10, 7, 12), (64, Q50, 10, 7, 5), (32, Q27, 11, 7, 4), (64, Q50, 10, 2, 3),
+                                                          (64, 1152921504606830593, 10, 7, 3), (32, 1073692673, 10, 7, 4), (64, Q50, 11, 7, 3)])
 def test_blind_rotate_matches_oracle(bits, q, log_n, log_basis, n_lwe):
     import torch
     import primus_fhe_b200 as P
