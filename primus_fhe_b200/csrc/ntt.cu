@@ -15,6 +15,8 @@
 
 #include <cuda.h>
 
+#include "tma.cuh"
+
 #include "internal.hpp"
 #include "host_math.hpp"
 
@@ -107,40 +109,6 @@ struct IoMaps {
     CUtensorMap in, out;
     const void *src;  // forward input (plain pointer: the forward transform reads with LDG)
 };
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// elected thread: shared (swizzled) -> global tensor rows [row, row + boxes*box_rows); returns once shared memory has been read
-__device__ __forceinline__ void tma_store_poly(const CUtensorMap *map, const void *sm, uint32_t row, int boxes, int box_rows) {
-    for (int bx = 0; bx < boxes; bx++)
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(0u), "r"(row + bx * box_rows),
-                     "r"(smem_addr(sm) + (uint32_t)bx * box_rows * 128u)
-                     : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-// elected thread: global tensor rows -> shared (swizzled), completion on the mbarrier
-__device__ __forceinline__ void tma_load_poly(const CUtensorMap *map, void *sm, uint32_t row, uint64_t *bar, int boxes, int box_rows) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"((uint32_t)(boxes * box_rows) * 128u) : "memory");
-    for (int bx = 0; bx < boxes; bx++)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                         smem_addr(sm) + (uint32_t)bx * box_rows * 128u),
-                     "l"(map), "r"(0u), "r"(row + bx * box_rows), "r"(smem_addr(bar))
-                     : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(smem_addr(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
 
 // ---- LSU-path kernels (every configuration) ----------------------------------------------------------------------------
 // PARAM_TB (forward, single modulus): table constants are read straight from the kernel-parameter bank instead of a
@@ -453,7 +421,7 @@ static TensorMapEncodeFn tensor_map_encoder() {
 
 
 // tensor map over a batch of polynomials viewed as 128-byte rows: {128/w, npolys * N*w/128}, box {128/w, min(rows, 256)}, SWIZZLE_128B
-template <typename T> static bool make_poly_map(CUtensorMap *map, const T *base, size_t npolys, int log_n) {
+template <typename T> bool make_poly_map(CUtensorMap *map, const T *base, size_t npolys, int log_n) {
     TensorMapEncodeFn enc = tensor_map_encoder();
     const uint64_t e = 128 / sizeof(T);  // words per 128-byte row
     const uint64_t rows = ((uint64_t)1 << log_n) / e, total_rows = (uint64_t)npolys * rows;
@@ -466,6 +434,8 @@ template <typename T> static bool make_poly_map(CUtensorMap *map, const T *base,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+template bool make_poly_map<uint32_t>(CUtensorMap *, const uint32_t *, size_t, int);
+template bool make_poly_map<uint64_t>(CUtensorMap *, const uint64_t *, size_t, int);
 
 template <typename F, int LOGN, int LOGE, int PPB>
 static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<typename F::WordT> *tables, int limbs,
