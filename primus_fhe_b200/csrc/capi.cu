@@ -569,6 +569,7 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
     if (batch == 0) return PFHE_OK;
     const size_t L = t->limbs.size(), n = t->limbs[0]->h.n, comps = (size_t)k + 1;
     if (L != r->moduli.size() || k < 1) return PFHE_ERR_INVALID_ARG;
+    if (k > 2) return PFHE_ERR_UNSUPPORTED;  // GLWE dimension 1 (RLWE) and 2, like the fused single-modulus kernel
     for (size_t i = 0; i < L; i++)
         if (t->limbs[i]->h.q != r->moduli[i]) return PFHE_ERR_INVALID_ARG;
     RnsDev<T> g;

@@ -135,33 +135,56 @@ __global__ void __launch_bounds__(128) rns_gadget_kernel(const __grid_constant__
 }
 
 // out[ct][c][limb][i] = sum_{r,l} digits[ct][r][l][limb][i] * key[r][l][c][limb][i] mod q_limb  (NTT domain)
-template <typename T>
-__global__ void __launch_bounds__(256) rns_key_mac_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, int comps, uint32_t levels,
+// One thread owns VEC consecutive coefficients of one (ciphertext, limb) and ALL output components: every digit word is
+// read from HBM exactly once (16-byte loads), the key comes from L2, sums are lazy double words (<= 16 terms per Barrett
+// reduction, reduce_dot_product, primus_modulus/src/common/compact/slice.rs:371-401).
+template <typename T, int COMPS>
+__global__ void __launch_bounds__(256) rns_key_mac_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, uint32_t levels,
                                                           const T *__restrict__ digits, const T *__restrict__ key, T *__restrict__ out,
                                                           size_t n, size_t batch) {
     using W = typename WideOf<T>::type;
-    const size_t per_ct = (size_t)comps * limbs * n, total = batch * per_ct;
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) V {
+        T v[VEC];
+    };
+    const size_t nv = n / VEC, per_ct = (size_t)limbs * nv, total = batch * per_ct;
     for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
         const size_t ct = gid / per_ct, rem = gid % per_ct;
-        const int c = (int)(rem / ((size_t)limbs * n));
-        const int limb = (int)((rem / n) % limbs);
-        const size_t i = rem % n;
+        const int limb = (int)(rem / nv);
+        const size_t i = (rem % nv) * VEC;
         const Barrett<T> br = lc.br[limb];
-        W acc = 0;
+        W acc[COMPS][VEC];
+#pragma unroll
+        for (int c = 0; c < COMPS; c++)
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[c][k] = 0;
         uint32_t terms = 0;
-        for (int r = 0; r < comps; r++) {
+        for (int r = 0; r < COMPS; r++) {
             for (uint32_t l = 0; l < levels; l++) {
-                const T d = digits[(((ct * comps + r) * levels + l) * limbs + limb) * n + i];
-                const T k = key[((((size_t)r * levels + l) * comps + c) * limbs + limb) * n + i];
-                if (terms == 16) {  // reduce_dot_product chunking (compact/mod.rs:14)
-                    acc = barrett_reduce_wide(br, (T)acc, (T)(acc >> (sizeof(T) * 8)));
+                const V d = *reinterpret_cast<const V *>(digits + ((((ct * COMPS + r) * levels + l) * limbs + limb) * n + i));
+                if (terms == 16) {
+#pragma unroll
+                    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+                        for (int k = 0; k < VEC; k++) acc[c][k] = barrett_reduce_wide(br, (T)acc[c][k], (T)(acc[c][k] >> (sizeof(T) * 8)));
                     terms = 1;
                 }
-                acc += (W)d * k;
                 terms++;
+#pragma unroll
+                for (int c = 0; c < COMPS; c++) {
+                    const V kv = *reinterpret_cast<const V *>(key + (((((size_t)r * levels + l) * COMPS + c) * limbs + limb) * n + i));
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) acc[c][k] += (W)d.v[k] * kv.v[k];
+                }
             }
         }
-        out[gid] = barrett_reduce_wide(br, (T)acc, (T)(acc >> (sizeof(T) * 8)));
+#pragma unroll
+        for (int c = 0; c < COMPS; c++) {
+            V o;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) o.v[k] = barrett_reduce_wide(br, (T)acc[c][k], (T)(acc[c][k] >> (sizeof(T) * 8)));
+            *reinterpret_cast<V *>(out + (((ct * COMPS + c) * limbs + limb) * n + i)) = o;
+        }
     }
 }
 
@@ -525,7 +548,14 @@ template <typename T>
 cudaError_t launch_rns_key_mac(const LimbConsts<T> &lc, int limbs, int comps, uint32_t levels, const T *digits, const T *key, T *out, size_t n,
                                size_t batch, cudaStream_t s) {
     if (!batch) return cudaSuccess;
-    rns_key_mac_kernel<T><<<grid_for(batch * comps * limbs * n, 256), 256, 0, s>>>(lc, limbs, comps, levels, digits, key, out, n, batch);
+    const size_t threads_total = batch * limbs * (n / (16 / sizeof(T)));
+    if (n % (16 / sizeof(T))) return cudaErrorNotSupported;
+    if (comps == 2)
+        rns_key_mac_kernel<T, 2><<<grid_for(threads_total, 256), 256, 0, s>>>(lc, limbs, levels, digits, key, out, n, batch);
+    else if (comps == 3)
+        rns_key_mac_kernel<T, 3><<<grid_for(threads_total, 256), 256, 0, s>>>(lc, limbs, levels, digits, key, out, n, batch);
+    else
+        return cudaErrorNotSupported;
     count_launch();
     return cudaGetLastError();
 }
