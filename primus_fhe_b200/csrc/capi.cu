@@ -248,6 +248,8 @@ template <typename T> struct DcrtHandle {
     int device = 0;
     std::vector<NttHandle<T> *> limbs;
     DevNtt<T> *d_tables = nullptr;  // device array of the limb tables
+    DevNtt<T> *d_tables_lat = nullptr;  // same limbs, lattice-kernel pass layout (nullptr: unsupported degree)
+    int lat_policy = 0;                 // field policy of the fused multi-limb external product (internal.hpp)
     DevNtt<T> tb0{};                // limb 0 by value (same field-policy flag as the device array)
 };
 
@@ -452,11 +454,27 @@ static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size
         d->tb0 = tabs[0];
         cudaError_t e = cudaMalloc(&d->d_tables, tabs.size() * sizeof(DevNtt<T>));
         if (e == cudaSuccess) e = cudaMemcpy(d->d_tables, tabs.data(), tabs.size() * sizeof(DevNtt<T>), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && d->limbs[0]->dev_lat.loge != 0) {
+            std::vector<DevNtt<T>> lat;
+            bool all_f64_lat = true, all_wide = sizeof(T) == 4;
+            for (auto *h : d->limbs) {
+                all_f64_lat = all_f64_lat && h->dev_lat.use_f64;
+                all_wide = all_wide && dcrt_wide32_ok((uint64_t)h->h.q, (int)log_n);
+            }
+            for (auto *h : d->limbs) {
+                lat.push_back(h->dev_lat);
+                lat.back().use_f64 = all_f64_lat ? 1u : 0u;
+            }
+            d->lat_policy = all_f64_lat ? 1 : (all_wide ? 2 : 0);
+            e = cudaMalloc(&d->d_tables_lat, lat.size() * sizeof(DevNtt<T>));
+            if (e == cudaSuccess) e = cudaMemcpy(d->d_tables_lat, lat.data(), lat.size() * sizeof(DevNtt<T>), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) s = cuda_fail(e);
     }
     if (s != PFHE_OK) {
         for (auto *h : d->limbs) destroy_handle(static_cast<H *>(h));
         if (d->d_tables) cudaFree(d->d_tables);
+        if (d->d_tables_lat) cudaFree(d->d_tables_lat);
         delete d;
         return s;
     }
@@ -590,6 +608,12 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
         T *cout = out + done * glwe_len;
         // digits of every input component: [ct][r][level][limb][n]
         PFHE_CUDA(launch_rns_gadget<T>(g, cin, digits, n, nb * comps, L * n, (size_t)g.levels * L * n, s));
+        static const bool unfused = getenv("PFHE_DCRT_EP_UNFUSED") != nullptr;  // A/B tuning hook
+        if (t->d_tables_lat && !unfused) {  // one fused kernel per (ciphertext, limb): digits read once, nothing written back
+            PFHE_CUDA(launch_dcrt_external_product<T>(t->lat_policy, t->d_tables_lat, (int)L, t->limbs[0]->h.log_n, k, g.levels, key, digits,
+                                                      cout, nb, to_coeff != 0, s));
+            continue;
+        }
         PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)L, digits, digits, nb * comps * g.levels * L, true, s));
         PFHE_CUDA(launch_rns_key_mac<T>(lc, (int)L, (int)comps, g.levels, digits, key, cout, n, nb, s));
         if (to_coeff) PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)L, cout, cout, nb * comps * L, false, s));
@@ -699,6 +723,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         if (t->d_tables) {                                                                                                            \
             DeviceGuard guard(t->device);                                                                                             \
             cudaFree(t->d_tables);                                                                                                    \
+            if (t->d_tables_lat) cudaFree(t->d_tables_lat);                                                                           \
         }                                                                                                                             \
         delete t;                                                                                                                     \
     }                                                                                                                                 \

@@ -71,6 +71,13 @@ template <typename T>
 cudaError_t launch_blind_rotate(const DevNtt<T> &tb, const GadgetParams<T> &g, const T *bsk, uint32_t n_lwe,
                                 const uint32_t *lwe, const T *test_vector, T *acc_out, size_t batch, cudaStream_t stream);
 
+// multi-limb external product from precomputed lifted digits, fused per (ciphertext, limb); `tables` = device array of the
+// limbs' lattice-layout tables; policy: 0 integer pipe, 1 lazy FP64, 2 wide u32 forward butterflies
+template <typename T>
+cudaError_t launch_dcrt_external_product(int policy, const DevNtt<T> *tables, int limbs, uint32_t log_n, uint32_t k, uint32_t levels,
+                                         const T *key, const T *digits, T *out, size_t batch, bool to_coeff, cudaStream_t stream);
+bool dcrt_wide32_ok(uint64_t q, int logn);
+
 cudaError_t run_modmul_microbench(int kind, uint32_t blocks, uint32_t iters, float *ms);
 
 }  // namespace pfhe

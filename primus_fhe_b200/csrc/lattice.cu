@@ -398,6 +398,139 @@ static cudaError_t run_br(const DevNtt<T> &tb, const GadgetParams<T> &g, const T
     return run_br_f<IntField<T>, LOGN, LOGE, PPB, MINB>(tb, g, bsk, n_lwe, lwe, tv, acc_out, batch, stream);
 }
 
+// ---- multi-limb (L > 1) external product, fused per (ciphertext, limb) ----------------------------------------------
+// The digits of CrtGlwe::mul_dcrt_ggsw_to depend on ALL limbs of a coefficient (compose -> multi-word gadget), so they are
+// produced once by rns_gadget_kernel (rns.cu) as lifted residues [ct][r][level][limb][N]; from there every limb is an
+// independent single-modulus problem: this kernel reads each digit polynomial ONCE, transforms it in registers,
+// multiply-accumulates it against key[r][level][c][limb] and writes only the k+1 output polynomials of its limb
+// (add_dcrt_glev_mul_crt_poly_assign, primus_lattice/src/glwe/dcrt.rs:178-255, restricted to one limb).
+template <typename F, int LOGN, int LOGE, int COMPS>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)), ep_min_blocks<LOGN, LOGE, 1>())
+dcrt_external_product_kernel(const DevNtt<typename F::WordT> *__restrict__ tables, int limbs, uint32_t levels,
+                             const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ digits,
+                             typename F::WordT *__restrict__ out, int to_coeff) {
+    using EP = ExtProd<F, LOGN, LOGE, COMPS>;
+    using Core = typename EP::Core;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    using LA = LatAcc<F>;
+    constexpr int N = EP::N, E = EP::E, CW = EP::CW, NV = EP::NV, FB0 = EP::FB0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw);
+    const int t = threadIdx.x;
+    const size_t ct = blockIdx.x / (unsigned)limbs;
+    const int limb = (int)(blockIdx.x % (unsigned)limbs);
+    const DevNtt<T> tb = tables[limb];
+    const typename F::Ctx cx = F::ctx(tb);
+    LSyncBlock sync;
+    typename EP::Acc acc[COMPS][E];
+#pragma unroll
+    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+        for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
+    uint32_t terms = 0;
+#pragma unroll 1
+    for (int r = 0; r < COMPS; r++) {
+#pragma unroll 1
+        for (uint32_t l = 0; l < levels; l++) {
+            const T *dig = digits + ((((ct * COMPS + r) * levels + l) * limbs + limb) * (size_t)N);
+            Elem x[E];
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::load(ldg_stream(dig + Core::elem_index(FB0, t, j)), cx);
+            Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
+            if (LA::kRenorm) {
+                if (terms == LA::kRenormEvery) {
+#pragma unroll
+                    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+                        for (int j = 0; j < E; j++) LA::renorm(acc[c][j], cx);
+                    terms = 1;
+                }
+                terms++;
+            }
+#pragma unroll
+            for (int c = 0; c < COMPS; c++) {
+                const T *kp = key + (((((size_t)r * levels + l) * COMPS + c) * limbs + limb) * (size_t)N) + (size_t)t * E;
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const typename Core::WVec kv = ldg_vec(reinterpret_cast<const typename Core::WVec *>(kp) + v);
+#pragma unroll
+                    for (int w = 0; w < CW; w++) LA::mac(acc[c][v * CW + w], x[v * CW + w], kv.v[w], cx);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COMPS; c++) {
+        T *o = out + (((ct * COMPS + c) * limbs + limb) * (size_t)N);
+        Elem x[E];
+        if (to_coeff) {
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::from_mac(LA::final(acc[c][j], cx), cx);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, cx, t, sync);
+            Core::inv_regs_to_global(x, o, cx, t);
+            sync();
+        } else {
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::mac_bits(LA::final(acc[c][j], cx), cx);
+            Core::template sm_store<Core::P::NPASS - 1>(x, sm, t);
+            sync();
+            Core::copy_s2g(sm, o, t);
+            sync();
+        }
+    }
+}
+
+template <typename F, int LOGN, int LOGE, int COMPS>
+static cudaError_t run_dcrt_ep_f(const DevNtt<typename F::WordT> *tables, int limbs, uint32_t levels, const typename F::WordT *key,
+                                 const typename F::WordT *digits, typename F::WordT *out, size_t batch, bool to_coeff, cudaStream_t stream) {
+    using T = typename F::WordT;
+    constexpr int threads = 1 << (LOGN - LOGE);
+    constexpr size_t smem = sizeof(T) * ((size_t)1 << LOGN);
+    auto k = dcrt_external_product_kernel<F, LOGN, LOGE, COMPS>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)(batch * limbs), threads, smem, stream>>>(tables, limbs, levels, key, digits, out, to_coeff ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+// policy: 0 = integer pipe, 1 = lazy FP64 (every limb < 2^50), 2 = wide u32 forward (every limb passes wide32_ok)
+template <typename T, int LOGN, int COMPS>
+static cudaError_t run_dcrt_ep(int policy, const DevNtt<T> *tables, int limbs, uint32_t levels, const T *key, const T *digits, T *out,
+                               size_t batch, bool to_coeff, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (policy == 1) return run_dcrt_ep_f<F64LazyField, LOGN, 3, COMPS>(tables, limbs, levels, key, digits, out, batch, to_coeff, stream);
+    } else {
+        if (policy == 2) return run_dcrt_ep_f<IntWide32Field, LOGN, 3, COMPS>(tables, limbs, levels, key, digits, out, batch, to_coeff, stream);
+    }
+    return run_dcrt_ep_f<IntField<T>, LOGN, 3, COMPS>(tables, limbs, levels, key, digits, out, batch, to_coeff, stream);
+}
+bool dcrt_wide32_ok(uint64_t q, int logn) { return wide32_ok(q, logn); }
+
+template <typename T>
+cudaError_t launch_dcrt_external_product(int policy, const DevNtt<T> *tables, int limbs, uint32_t log_n, uint32_t k, uint32_t levels,
+                                         const T *key, const T *digits, T *out, size_t batch, bool to_coeff, cudaStream_t s) {
+    if (batch == 0) return cudaSuccess;
+#define PFHE_DEP_CASE(LOGN)                                                                                                           \
+    case LOGN:                                                                                                                        \
+        if (k == 1) return run_dcrt_ep<T, LOGN, 2>(policy, tables, limbs, levels, key, digits, out, batch, to_coeff, s);              \
+        if (k == 2) return run_dcrt_ep<T, LOGN, 3>(policy, tables, limbs, levels, key, digits, out, batch, to_coeff, s);              \
+        break;
+    switch (log_n) {
+        PFHE_DEP_CASE(10)
+        PFHE_DEP_CASE(11)
+        PFHE_DEP_CASE(12)
+    }
+#undef PFHE_DEP_CASE
+    return cudaErrorNotSupported;
+}
+template cudaError_t launch_dcrt_external_product<uint32_t>(int, const DevNtt<uint32_t> *, int, uint32_t, uint32_t, uint32_t, const uint32_t *,
+                                                            const uint32_t *, uint32_t *, size_t, bool, cudaStream_t);
+template cudaError_t launch_dcrt_external_product<uint64_t>(int, const DevNtt<uint64_t> *, int, uint32_t, uint32_t, uint32_t, const uint64_t *,
+                                                            const uint64_t *, uint64_t *, size_t, bool, cudaStream_t);
+
 // The lattice kernels use their own (smaller) register tile: DevNtt::fwd_pass/inv_pass must have been laid
 // out for lattice_loge(bits, log_n) -- capi.cu passes the matching DevNtt view.
 int lattice_loge(int bits, int log_n) {
