@@ -230,6 +230,13 @@ pfhe_status pfhe_mod32_slice_op_host(pfhe_slice_op op, const uint32_t *moduli, s
                                      const uint32_t *a, const uint32_t *b, const uint32_t *c, uint32_t *out,
                                      size_t rows, size_t n);
 
+/* MultiplyFactor::new(operand, bit_shift, modulus) (primus_factor/src/mul_factor/mod.rs:4-43): the HEXL-style precomputed
+ * quotient floor(operand * 2^bit_shift / modulus) (low 64 bits), bit_shift in {32, 52, 64}; setup-only host arithmetic (the
+ * device tables use the same quotient with bit_shift = word size).  INVALID_ARG mirrors the constructor's asserts. */
+pfhe_status pfhe_multiply_factor64(uint64_t operand, uint32_t bit_shift, uint64_t modulus, uint64_t *quotient);
+/* MultiplyFactor::mul_modulo::<BIT_SHIFT> (mul_factor/mod.rs:45-70) for one value, host side (table-construction helper). */
+pfhe_status pfhe_multiply_factor64_mul(uint64_t operand, uint64_t quotient, uint32_t bit_shift, uint64_t b, uint64_t modulus, uint64_t *out);
+
 /* ===================================================================================== */
 /* Gadget decomposition and RNS limb handling                                             */
 /* ===================================================================================== */

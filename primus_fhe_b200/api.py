@@ -576,6 +576,25 @@ def dot_product_batch(q, a, b, out, n, bits=64):
     check(f(int(q), _dev_ptr(a, bits), _dev_ptr(b, bits, a.numel()), _dev_ptr(out, bits, rows), rows, n, _stream()))
 
 
+class MultiplyFactor:
+    """MultiplyFactor (primus_factor/src/mul_factor/mod.rs:4-88): operand with its precomputed quotient for bit shift 32/52/64."""
+
+    def __init__(self, operand, bit_shift, modulus):
+        q = C.c_uint64(0)
+        f = lib().pfhe_multiply_factor64; f.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p]
+        check(f(int(operand), int(bit_shift), int(modulus), C.byref(q)))
+        self._operand, self._quotient, self.bit_shift, self.modulus = int(operand), int(q.value), int(bit_shift), int(modulus)
+
+    def operand(self): return self._operand
+    def quotient(self): return self._quotient
+
+    def mul_modulo(self, b):
+        out = C.c_uint64(0)
+        f = lib().pfhe_multiply_factor64_mul; f.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+        check(f(self._operand, self._quotient, self.bit_shift, int(b), self.modulus, C.byref(out)))
+        return int(out.value)
+
+
 def extract_lwe_batch(q, rlwe, lwe, n, bits=64):
     """Rlwe::extract_lwe (primus_lattice/src/rlwe/coeff.rs:264-288) over a batch."""
     f = getattr(lib(), f"pfhe_extract_lwe{bits}_batch")

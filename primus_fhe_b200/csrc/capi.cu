@@ -931,6 +931,20 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
 PFHE_DEFINE_WORD(32, uint32_t)
 PFHE_DEFINE_WORD(64, uint64_t)
 
+pfhe_status pfhe_multiply_factor64(uint64_t operand, uint32_t bit_shift, uint64_t modulus, uint64_t *quotient) {
+    if (!quotient || modulus == 0 || operand >= modulus || (bit_shift != 32 && bit_shift != 52 && bit_shift != 64)) return PFHE_ERR_INVALID_ARG;
+    const unsigned __int128 n = (unsigned __int128)operand << bit_shift;  // (op_hi, op_lo) of mul_factor/mod.rs:21-28
+    *quotient = (uint64_t)(n / modulus);
+    return PFHE_OK;
+}
+pfhe_status pfhe_multiply_factor64_mul(uint64_t operand, uint64_t quotient, uint32_t bit_shift, uint64_t b, uint64_t modulus, uint64_t *out) {
+    if (!out || (bit_shift != 32 && bit_shift != 52 && bit_shift != 64)) return PFHE_ERR_INVALID_ARG;
+    const uint64_t hw = bit_shift == 32 ? (quotient * b) >> 32 : (uint64_t)(((unsigned __int128)quotient * b) >> bit_shift);
+    const uint64_t r = operand * b - modulus * hw;  // lazy_mul_modulo, wrapping
+    const uint64_t r2 = r - modulus;
+    *out = r < r2 ? r : r2;                          // r.min(r.wrapping_sub(modulus))
+    return PFHE_OK;
+}
 pfhe_status pfhe_device_count(int *count) {
     if (!count) return PFHE_ERR_INVALID_ARG;
     PFHE_CUDA(cudaGetDeviceCount(count));

@@ -49,3 +49,22 @@ def test_geometry_and_status_paths_without_gpu():
         lib.pfhe_ntt64_create.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
         rc = lib.pfhe_ntt64_create(0, 12, 1125899906826241, C.byref(h))
         assert rc == 8 and not h.value           # PFHE_ERR_CUDA: the product path refuses to run without a GPU
+
+
+def test_multiply_factor_matches_reference_tests():
+    """MultiplyFactor (primus_factor/src/mul_factor/mod.rs:95-147: test_32 / test_52 / test_64): host-side setup arithmetic,
+    callable without a GPU; checked against exact big-int products on seeded inputs."""
+    import numpy as np
+    import primus_fhe_b200 as P
+    rng = np.random.default_rng(52)
+    for q, shift in ((536813569, 32), (562949953392641, 52), (1152921504606830593, 64)):
+        for _ in range(300):
+            a, b = int(rng.integers(0, q)), int(rng.integers(0, q))
+            mf = P.MultiplyFactor(a, shift, q)
+            assert mf.quotient() == ((a << shift) // q) & ((1 << 64) - 1)
+            assert mf.mul_modulo(b) == a * b % q
+    import pytest
+    with pytest.raises(P.PfheError):
+        P.MultiplyFactor(5, 40, 17)          # "Unsupported BitShift"
+    with pytest.raises(P.PfheError):
+        P.MultiplyFactor(17, 64, 17)         # operand must be less than modulus
