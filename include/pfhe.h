@@ -197,7 +197,10 @@ typedef enum {
     PFHE_OP_FACTOR_MUL = 9,  /* out = f*a  (Shoup) FactorSliceOps::factor_mul_slice_to (primus_factor/src/ops.rs:58-118) */
     PFHE_OP_ADD_FACTOR_MUL = 10, /* out += f*a     add_factor_mul_slice_assign (common/slice.rs:61-70)   */
     PFHE_OP_SUB_FACTOR_MUL = 11, /* out -= f*a     sub_factor_mul_slice_assign                   */
-    PFHE_OP_REDUCE_LAZY = 12     /* out = a mod q for a in [0,4q): canonicalises lazy-range inputs (reduce_once twice) */
+    PFHE_OP_REDUCE_LAZY = 12,    /* out = a mod q for a in [0,4q): canonicalises lazy-range inputs (reduce_once twice) */
+    PFHE_OP_DOUBLE = 13,         /* out = 2a           reduce_double_slice_to (slice_ops.rs:91-100)                */
+    PFHE_OP_MUL_SCALAR_ADD = 14, /* out = a*s + c      reduce_mul_scalar_add_slice_to (slice_ops.rs:229)           */
+    PFHE_OP_FACTOR_MUL_ADD = 15  /* out = f*a + c (Shoup) FactorSliceOps::factor_mul_add_slice_to (ops.rs:117)     */
 } pfhe_slice_op;
 
 /* One entry point per word size; `scalars` (HOST, `limbs` words) holds s / f per limb for the

@@ -27,6 +27,7 @@ from ._cabi import PfheError, check, lib
 
 OP_MUL, OP_ADD_MUL, OP_SUB_MUL, OP_MUL_ADD, OP_ADD, OP_SUB, OP_NEG = range(7)
 OP_MUL_SCALAR, OP_ADD_MUL_SCALAR, OP_FACTOR_MUL, OP_ADD_FACTOR_MUL, OP_SUB_FACTOR_MUL = range(7, 12)
+OP_REDUCE_LAZY, OP_DOUBLE, OP_MUL_SCALAR_ADD, OP_FACTOR_MUL_ADD = range(12, 16)
 
 
 def _ct(bits):
@@ -342,6 +343,11 @@ class BarrettModulus:
 
     def reduce_mul_scalar_slice_to(self, a, scalar, out):
         return self._run(OP_MUL_SCALAR, a, None, None, out, self._sc(scalar))
+
+    def reduce_double_slice_to(self, a, out): return self._run(OP_DOUBLE, a, None, None, out)
+    def reduce_sub_slice_rev_assign(self, a, b): return self._run(OP_SUB, a, b, None, b)          # b = a - b
+    def reduce_mul_scalar_add_slice_to(self, a, scalar, c, out): return self._run(OP_MUL_SCALAR_ADD, a, None, c, out, self._sc(scalar))
+    def factor_mul_add_slice_to(self, factor, rhs, addend, out): return self._run(OP_FACTOR_MUL_ADD, rhs, None, addend, out, self._sc(factor))
 
     def reduce_add_mul_scalar_slice_assign(self, acc, a, scalar):
         return self._run(OP_ADD_MUL_SCALAR, a, None, None, acc, self._sc(scalar))

@@ -375,7 +375,8 @@ template <typename T> static pfhe_status make_limb_consts(const T *moduli, size_
     constexpr int BITS = sizeof(T) * 8;
     if (!moduli || limbs == 0 || limbs > (size_t)kMaxLimbs) return PFHE_ERR_INVALID_ARG;
     const bool needs_scalar = op == PFHE_OP_MUL_SCALAR || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_FACTOR_MUL ||
-                              op == PFHE_OP_ADD_FACTOR_MUL || op == PFHE_OP_SUB_FACTOR_MUL;
+                              op == PFHE_OP_ADD_FACTOR_MUL || op == PFHE_OP_SUB_FACTOR_MUL || op == PFHE_OP_MUL_SCALAR_ADD ||
+                              op == PFHE_OP_FACTOR_MUL_ADD;
     if (needs_scalar && !scalars) return PFHE_ERR_INVALID_ARG;
     for (size_t i = 0; i < limbs; i++) {
         const T q = moduli[i];
@@ -393,11 +394,11 @@ template <typename T> static pfhe_status make_limb_consts(const T *moduli, size_
 template <typename T>
 static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
                                 size_t n, void *stream) {
-    if (op < 0 || op > PFHE_OP_REDUCE_LAZY) return PFHE_ERR_INVALID_ARG;
+    if (op < 0 || op > PFHE_OP_FACTOR_MUL_ADD) return PFHE_ERR_INVALID_ARG;
     if (rows * n == 0) return PFHE_OK;
     if (!a || !out) return PFHE_ERR_INVALID_ARG;
     if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
-    if (op == PFHE_OP_MUL_ADD && !c) return PFHE_ERR_INVALID_ARG;
+    if ((op == PFHE_OP_MUL_ADD || op == PFHE_OP_MUL_SCALAR_ADD || op == PFHE_OP_FACTOR_MUL_ADD) && !c) return PFHE_ERR_INVALID_ARG;
     LimbConsts<T> lc;
     pfhe_status s = make_limb_consts<T>(moduli, limbs, scalars, op, lc);
     if (s != PFHE_OK) return s;
@@ -496,17 +497,17 @@ template <typename T, typename D> static pfhe_status dcrt_host_transform(const D
 template <typename T>
 static pfhe_status slice_op_host(int op, const T *moduli, size_t limbs, const T *scalars, const T *a, const T *b, const T *c, T *out, size_t rows,
                                  size_t n) {
-    if (op < 0 || op > PFHE_OP_REDUCE_LAZY) return PFHE_ERR_INVALID_ARG;
+    if (op < 0 || op > PFHE_OP_FACTOR_MUL_ADD) return PFHE_ERR_INVALID_ARG;
     if (rows * n == 0) return PFHE_OK;
     if (!a || !out) return PFHE_ERR_INVALID_ARG;
     if (op <= PFHE_OP_SUB && !b) return PFHE_ERR_INVALID_ARG;
-    if (op == PFHE_OP_MUL_ADD && !c) return PFHE_ERR_INVALID_ARG;
+    if ((op == PFHE_OP_MUL_ADD || op == PFHE_OP_MUL_SCALAR_ADD || op == PFHE_OP_FACTOR_MUL_ADD) && !c) return PFHE_ERR_INVALID_ARG;
     LimbConsts<T> lc;
     pfhe_status s = make_limb_consts<T>(moduli, limbs, scalars, op, lc);
     if (s != PFHE_OK) return s;
     const bool acc = op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_ADD_FACTOR_MUL ||
                      op == PFHE_OP_SUB_FACTOR_MUL;
-    const bool rb = op <= PFHE_OP_SUB, rc = op == PFHE_OP_MUL_ADD;
+    const bool rb = op <= PFHE_OP_SUB, rc = op == PFHE_OP_MUL_ADD || op == PFHE_OP_MUL_SCALAR_ADD || op == PFHE_OP_FACTOR_MUL_ADD;
     const size_t bytes = sizeof(T) * limbs * n;
     const void *ins[4];
     size_t inb[4];

@@ -42,12 +42,15 @@ __device__ __forceinline__ T apply_op(const Barrett<T> &br, T s, T sq, T a, T b,
         case PFHE_OP_ADD_FACTOR_MUL: return mod_add<T>(o, shoup<T>(a, s, sq, q), q);
         case PFHE_OP_SUB_FACTOR_MUL: return mod_sub<T>(o, shoup<T>(a, s, sq, q), q);
         case PFHE_OP_REDUCE_LAZY: return csub<T>(csub<T>(a, q + q), q);
+        case PFHE_OP_DOUBLE: return mod_add<T>(a, a, q);
+        case PFHE_OP_MUL_SCALAR_ADD: return barrett_mul_add<T>(br, a, s, c);
+        case PFHE_OP_FACTOR_MUL_ADD: return mod_add<T>(shoup<T>(a, s, sq, q), c, q);
     }
     return 0;
 }
 
 constexpr bool op_reads_b(int op) { return op == PFHE_OP_MUL || op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_MUL_ADD || op == PFHE_OP_ADD || op == PFHE_OP_SUB; }
-constexpr bool op_reads_c(int op) { return op == PFHE_OP_MUL_ADD; }
+constexpr bool op_reads_c(int op) { return op == PFHE_OP_MUL_ADD || op == PFHE_OP_MUL_SCALAR_ADD || op == PFHE_OP_FACTOR_MUL_ADD; }
 constexpr bool op_reads_out(int op) { return op == PFHE_OP_ADD_MUL || op == PFHE_OP_SUB_MUL || op == PFHE_OP_ADD_MUL_SCALAR || op == PFHE_OP_ADD_FACTOR_MUL || op == PFHE_OP_SUB_FACTOR_MUL; }
 
 // slices are [rows][limbs][n]; vectorised when n % W == 0 (always true for polynomial lengths >= 4)
@@ -187,6 +190,9 @@ cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T 
         PFHE_CASE(PFHE_OP_ADD_FACTOR_MUL)
         PFHE_CASE(PFHE_OP_SUB_FACTOR_MUL)
         PFHE_CASE(PFHE_OP_REDUCE_LAZY)
+        PFHE_CASE(PFHE_OP_DOUBLE)
+        PFHE_CASE(PFHE_OP_MUL_SCALAR_ADD)
+        PFHE_CASE(PFHE_OP_FACTOR_MUL_ADD)
 #undef PFHE_CASE
     }
     return cudaErrorInvalidValue;

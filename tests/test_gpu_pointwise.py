@@ -177,3 +177,32 @@ def test_inv_slice_matches_bigint(bits, q):
     a[7] = 0; a[300] = 0                                   # try_reduce_inv_slice_to -> NoInverseAtIndex { index: 7 }
     assert P.inv_slice_batch(q, _dev(a), out, bits) == 7
     assert int(out.cpu().numpy().view(dt)[7]) == 0
+
+
+@pytest.mark.parametrize("bits,q", [(64, 1125899906826241), (64, 1152921504606830593), (32, 132120577)])
+def test_remaining_slice_ops_match_bigint(bits, q):
+    """reduce_double_slice_to, reduce_sub_slice_rev_assign, reduce_mul_scalar_add_slice_to (primus_reduce/src/slice_ops.rs:91-133,
+    :229) and FactorSliceOps::factor_mul_add_slice_to (primus_factor/src/ops.rs:117): exact big-int check, device and host shims."""
+    import torch
+    import primus_fhe_b200 as P
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(12)
+    n = 1000
+    a = rng.integers(0, q, n, dtype=np.uint64).astype(dt); b = rng.integers(0, q, n, dtype=np.uint64).astype(dt)
+    c = rng.integers(0, q, n, dtype=np.uint64).astype(dt)
+    a[0], b[0], c[0] = q - 1, q - 1, q - 1
+    s = int(rng.integers(1, q))
+    m = P.BarrettModulus(q, bits)
+    A, B, Cc = [int(v) for v in a], [int(v) for v in b], [int(v) for v in c]
+    for host in (False, True):
+        conv = (lambda x: x.copy()) if host else (lambda x: _dev(x.copy()))
+        back = (lambda t: t) if host else (lambda t: t.cpu().numpy().view(dt))
+        out = conv(np.zeros(n, dtype=dt))
+        m.reduce_double_slice_to(conv(a), out)
+        assert [int(v) for v in back(out)] == [2 * x % q for x in A]
+        bb = conv(b); m.reduce_sub_slice_rev_assign(conv(a), bb)
+        assert [int(v) for v in back(bb)] == [(x - y) % q for x, y in zip(A, B)]
+        m.reduce_mul_scalar_add_slice_to(conv(a), s, conv(c), out)
+        assert [int(v) for v in back(out)] == [(x * s + z) % q for x, z in zip(A, Cc)]
+        m.factor_mul_add_slice_to(s, conv(a), conv(c), out)
+        assert [int(v) for v in back(out)] == [(x * s + z) % q for x, z in zip(A, Cc)]
