@@ -297,6 +297,10 @@ pfhe_status pfhe_blind_rotate32_batch(const pfhe_ntt32 *t, uint32_t log_basis, u
 /* Rlwe::extract_lwe (primus_lattice/src/rlwe/coeff.rs:264-288): rlwe [batch][2][N] -> lwe [batch][N+1] */
 pfhe_status pfhe_extract_lwe64_batch(uint64_t q, const uint64_t *rlwe, uint64_t *lwe, size_t n, size_t batch, void *stream);
 pfhe_status pfhe_extract_lwe32_batch(uint32_t q, const uint32_t *rlwe, uint32_t *lwe, size_t n, size_t batch, void *stream);
+/* Rlwe::extract_lwe_with_index (coeff.rs:194-226; count = 1) and Rlwe::extract_first_few_lwe (coeff.rs:229-261; index = 0,
+ * MultiMsgLwe with `count` bodies): rlwe [batch][2][N] -> lwe [batch][N + count]; index + count <= N. */
+pfhe_status pfhe_extract_lwe64_ex_batch(uint64_t q, const uint64_t *rlwe, uint64_t *lwe, size_t n, size_t batch, size_t index, size_t count, void *stream);
+pfhe_status pfhe_extract_lwe32_ex_batch(uint32_t q, const uint32_t *rlwe, uint32_t *lwe, size_t n, size_t batch, size_t index, size_t count, void *stream);
 
 
 /* ===================================================================================== */

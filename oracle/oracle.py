@@ -366,6 +366,28 @@ def extract_lwe(rlwe, q, bits=64):
 
 
 # --------------------------------------------------------------------------- decomposition
+def extract_lwe_with_index(rlwe, index, q):
+    """Rlwe::extract_lwe_with_index (primus_lattice/src/rlwe/coeff.rs:194-226), numpy restatement of its three copy loops."""
+    rlwe = np.asarray(rlwe); n = rlwe.size // 2; split = index + 1
+    out = np.empty(n + 1, dtype=rlwe.dtype)
+    out[:split] = rlwe[:split][::-1]
+    tail = rlwe[split:n][::-1]
+    out[split:n] = np.where(tail == 0, 0, q - tail).astype(rlwe.dtype)
+    out[n] = rlwe[n + index]
+    return out
+
+
+def extract_first_few_lwe(rlwe, count, q):
+    """Rlwe::extract_first_few_lwe (coeff.rs:229-261)."""
+    rlwe = np.asarray(rlwe); n = rlwe.size // 2
+    out = np.empty(n + count, dtype=rlwe.dtype)
+    out[0] = rlwe[0]
+    tail = rlwe[1:n][::-1]
+    out[1:n] = np.where(tail == 0, 0, q - tail).astype(rlwe.dtype)
+    out[n:] = rlwe[n:n + count]
+    return out
+
+
 class ApproxSignedBasis:
     """primus_decompose/src/primitive/basis.rs:12-407 (non-power-of-two modulus branch)."""
 

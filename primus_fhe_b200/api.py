@@ -609,6 +609,14 @@ def extract_lwe_batch(q, rlwe, lwe, n, bits=64):
     check(f(int(q), _dev_ptr(rlwe, bits), _dev_ptr(lwe, bits, batch * (n + 1)), n, batch, _stream()))
 
 
+def extract_lwe_ex_batch(q, rlwe, lwe, n, index=0, count=1, bits=64):
+    """Rlwe::extract_lwe_with_index (count = 1) / extract_first_few_lwe (index = 0) (primus_lattice/src/rlwe/coeff.rs:194-261)."""
+    f = getattr(lib(), f"pfhe_extract_lwe{bits}_ex_batch")
+    f.argtypes = [_ct(bits), C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    batch = rlwe.numel() // (2 * n)
+    check(f(int(q), _dev_ptr(rlwe, bits), _dev_ptr(lwe, bits, batch * (n + count)), n, batch, index, count, _stream()))
+
+
 def modmul_microbench(kind: int, blocks: int, iters: int, device: int = 0) -> float:
     ms = C.c_float(0)
     f = lib().pfhe_modmul_microbench

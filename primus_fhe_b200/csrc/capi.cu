@@ -822,7 +822,13 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_extract_lwe##B##_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, void *stream) {                       \
         if ((!rlwe || !lwe) && batch) return PFHE_ERR_INVALID_ARG;                                                                    \
-        PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, static_cast<cudaStream_t>(stream)));                                  \
+        PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, 0, 1, static_cast<cudaStream_t>(stream)));                            \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
+    pfhe_status pfhe_extract_lwe##B##_ex_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, size_t index, size_t count,        \
+                                               void *stream) {                                                                        \
+        if (((!rlwe || !lwe) && batch) || count == 0 || index + count > n) return PFHE_ERR_INVALID_ARG;                               \
+        PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, index, count, static_cast<cudaStream_t>(stream)));                    \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_rns##B##_create(const T *moduli, size_t count, pfhe_rns##B **out) { return rns_create<T>(moduli, count, out); }  \

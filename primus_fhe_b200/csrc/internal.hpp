@@ -61,7 +61,7 @@ template <typename T>
 cudaError_t launch_rns_lift(const T *moduli_host, int limbs, T small_modulus, const T *small, T *out, size_t count,
                             cudaStream_t stream);
 template <typename T>
-cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, cudaStream_t stream);
+cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, size_t index, size_t count, cudaStream_t stream);
 
 // ---- lattice (lattice.cu) ---------------------------------------------------------------------
 template <typename T>

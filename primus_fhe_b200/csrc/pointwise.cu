@@ -308,27 +308,32 @@ template cudaError_t launch_rns_lift<uint32_t>(const uint32_t *, int, uint32_t, 
 template cudaError_t launch_rns_lift<uint64_t>(const uint64_t *, int, uint64_t, const uint64_t *, uint64_t *, size_t, cudaStream_t);
 
 // lwe = [a_0, -a_{N-1}, ..., -a_1, b_0]
+// Rlwe::extract_lwe_with_index / extract_first_few_lwe / extract_lwe (primus_lattice/src/rlwe/coeff.rs:194-288) in one kernel:
+// out[i] = a[index - i] for i <= index, -a[N + index - i] for index < i < N, then `count` body coefficients b[index ..].
+// (index = 0, count = 1: extract_lwe; count > 1: the MultiMsgLwe of extract_first_few_lwe.)
 template <typename T>
-__global__ void __launch_bounds__(256) extract_lwe_kernel(T q, const T *__restrict__ rlwe, T *__restrict__ lwe, size_t n, size_t batch) {
-    const size_t per = n + 1, total = batch * per;
+__global__ void __launch_bounds__(256) extract_lwe_kernel(T q, const T *__restrict__ rlwe, T *__restrict__ lwe, size_t n, size_t batch,
+                                                          size_t index, size_t count) {
+    const size_t per = n + count, total = batch * per;
     for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
         const size_t bidx = gid / per, i = gid % per;
         const T *src = rlwe + bidx * 2 * n;
         T v;
-        if (i == 0) v = src[0];
-        else if (i == n) v = src[n];
-        else v = mod_neg<T>(src[n - i], q);
+        if (i >= n) v = src[n + index + (i - n)];
+        else if (i <= index) v = src[index - i];
+        else v = mod_neg<T>(src[n + index - i], q);
         lwe[gid] = v;
     }
 }
-template <typename T> cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, cudaStream_t stream) {
+template <typename T>
+cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, size_t index, size_t count, cudaStream_t stream) {
     if (batch == 0) return cudaSuccess;
-    extract_lwe_kernel<T><<<stream_grid(batch * (n + 1), 256), 256, 0, stream>>>(q, rlwe, lwe, n, batch);
+    extract_lwe_kernel<T><<<stream_grid(batch * (n + count), 256), 256, 0, stream>>>(q, rlwe, lwe, n, batch, index, count);
     count_launch();
     return cudaGetLastError();
 }
-template cudaError_t launch_extract_lwe<uint32_t>(uint32_t, const uint32_t *, uint32_t *, size_t, size_t, cudaStream_t);
-template cudaError_t launch_extract_lwe<uint64_t>(uint64_t, const uint64_t *, uint64_t *, size_t, size_t, cudaStream_t);
+template cudaError_t launch_extract_lwe<uint32_t>(uint32_t, const uint32_t *, uint32_t *, size_t, size_t, size_t, size_t, cudaStream_t);
+template cudaError_t launch_extract_lwe<uint64_t>(uint64_t, const uint64_t *, uint64_t *, size_t, size_t, size_t, size_t, cudaStream_t);
 
 // ---- integer-pipe microbenchmark --------------------------------------------------------------------
 // 8 independent chains of Harvey butterflies per thread, registers only: measures the achievable

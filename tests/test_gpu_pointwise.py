@@ -206,3 +206,29 @@ def test_remaining_slice_ops_match_bigint(bits, q):
         assert [int(v) for v in back(out)] == [(x * s + z) % q for x, z in zip(A, Cc)]
         m.factor_mul_add_slice_to(s, conv(a), conv(c), out)
         assert [int(v) for v in back(out)] == [(x * s + z) % q for x, z in zip(A, Cc)]
+
+
+@pytest.mark.parametrize("bits,q,n", [(64, 1125899906826241, 1024), (32, 132120577, 512)])
+def test_extract_lwe_variants_match_oracle(bits, q, n):
+    """extract_lwe_with_index / extract_first_few_lwe (primus_lattice/src/rlwe/coeff.rs:194-261)."""
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(15)
+    batch = 4
+    rlwe = rng.integers(0, q, (batch, 2 * n), dtype=np.uint64).astype(dt)
+    rlwe[0, :5] = 0
+    d = _dev(rlwe)
+    for index in (0, 1, 17, n - 1):
+        out = torch.empty((batch, n + 1), dtype=d.dtype, device="cuda")
+        P.extract_lwe_ex_batch(q, d, out, n, index=index, count=1, bits=bits)
+        want = np.stack([O.extract_lwe_with_index(rlwe[b], index, q) for b in range(batch)])
+        assert np.array_equal(out.cpu().numpy().view(dt), want)
+    assert np.array_equal(np.stack([O.extract_lwe_with_index(rlwe[b], 0, q) for b in range(batch)]),
+                          np.stack([O.extract_lwe(rlwe[b], q, bits) for b in range(batch)]))
+    for count in (1, 3, n):
+        out = torch.empty((batch, n + count), dtype=d.dtype, device="cuda")
+        P.extract_lwe_ex_batch(q, d, out, n, index=0, count=count, bits=bits)
+        want = np.stack([O.extract_first_few_lwe(rlwe[b], count, q) for b in range(batch)])
+        assert np.array_equal(out.cpu().numpy().view(dt), want)
