@@ -211,6 +211,14 @@ pfhe_status pfhe_mod64_slice_op(pfhe_slice_op op, const uint64_t *moduli, size_t
 pfhe_status pfhe_mod32_slice_op(pfhe_slice_op op, const uint32_t *moduli, size_t limbs, const uint32_t *scalars,
                                 const uint32_t *a, const uint32_t *b, const uint32_t *c, uint32_t *out,
                                 size_t rows, size_t n, void *stream);
+/* NTT-domain ciphertext x polynomial (primus_lattice/src/rlwe/ntt.rs:78-152: mul_ntt_polynomial_assign / _to,
+ * add_ntt_rlwe_mul_ntt_polynomial_assign; the GLWE forms loop the same way): op in {PFHE_OP_MUL, PFHE_OP_ADD_MUL, PFHE_OP_SUB_MUL}
+ * with `b` broadcast -- row r of `a`/`out` ([rows][limbs][n]) pairs with row r / group of `b` ([rows/group][limbs][n]), group =
+ * components per ciphertext (2 for RLWE). */
+pfhe_status pfhe_mod64_slice_op_bcast(pfhe_slice_op op, const uint64_t *moduli, size_t limbs, const uint64_t *a, const uint64_t *b,
+                                      uint64_t *out, size_t rows, size_t n, size_t group, void *stream);
+pfhe_status pfhe_mod32_slice_op_bcast(pfhe_slice_op op, const uint32_t *moduli, size_t limbs, const uint32_t *a, const uint32_t *b,
+                                      uint32_t *out, size_t rows, size_t n, size_t group, void *stream);
 /* DcrtPolynomial::butterfly_mul_factor_to / DcrtGlwe::butterfly_mul_factor_to (primus_poly/src/dcrt/mul.rs:189-222,
  * primus_lattice/src/glwe/dcrt.rs:150-175): (a, out) = (a + s, (a_orig - s) * w) per limb; a, s, out: device [rows][limbs][n]
  * in [0,q), a updated in place; w: device [limbs][n] factor polynomial (values; the Shoup quotients of the reference's

@@ -6,5 +6,5 @@ The package holds only what the path needs: `csrc/` (CUDA kernels + the C-ABI of
 from ._cabi import PfheError, LIB_PATH, declared_symbols, launch_count  # noqa: F401
 from .api import (  # noqa: F401
     ApproxSignedBasis, BarrettModulus, BaseConverter, BigUintApproxSignedBasis, MultiplyFactor, RNSBase, U32DcrtTable, U32NttTable, U64DcrtTable, U64NttTable,
-    butterfly_mul_factor_batch, dcrt_external_product_batch, device_count, dot_product_batch, extract_lwe_batch, extract_lwe_ex_batch, inv_slice_batch, modmul_microbench, mul_monomial_batch,
+    butterfly_mul_factor_batch, dcrt_external_product_batch, device_count, dot_product_batch, extract_lwe_batch, extract_lwe_ex_batch, inv_slice_batch, modmul_microbench, mul_monomial_batch, slice_op_bcast,
 )

@@ -552,6 +552,17 @@ def mul_monomial_batch(moduli, degrees, polys, out, log_n, bits=64):
     check(f(m, L, _dev_ptr(degrees, 32, batch), _dev_ptr(polys, bits), _dev_ptr(out, bits, polys.numel()), log_n, batch, _stream()))
 
 
+def slice_op_bcast(op, moduli, a, b, out, n, group, bits=64):
+    """NTT-domain ciphertext x polynomial with `b` broadcast over the `group` components of each ciphertext
+    (primus_lattice/src/rlwe/ntt.rs:78-152). a, out: CUDA [rows][L][n]; b: CUDA [rows/group][L][n]; op in OP_MUL/OP_ADD_MUL/OP_SUB_MUL."""
+    L = len(moduli)
+    m = (_ct(bits) * L)(*[int(x) for x in moduli])
+    rows = a.numel() // (L * n)
+    f = getattr(lib(), f"pfhe_mod{bits}_slice_op_bcast")
+    f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    check(f(op, m, L, _dev_ptr(a, bits), _dev_ptr(b, bits, a.numel() // group), _dev_ptr(out, bits, a.numel()), rows, n, group, _stream()))
+
+
 def butterfly_mul_factor_batch(moduli, a, s, w, out, n, bits=64):
     """(a, out) = (a + s, (a - s) * w) per limb (primus_poly/src/dcrt/mul.rs:189-222). a, s, out: CUDA [rows][L][n]; w: CUDA [L][n]."""
     L = len(moduli)

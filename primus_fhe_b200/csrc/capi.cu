@@ -769,6 +769,18 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
                                             const T *b, const T *c, T *out, size_t rows, size_t n) {                                  \
         return slice_op_host<T>((int)op, moduli, limbs, scalars, a, b, c, out, rows, n);                                              \
     }                                                                                                                                 \
+    pfhe_status pfhe_mod##B##_slice_op_bcast(pfhe_slice_op op, const T *moduli, size_t limbs, const T *a, const T *b, T *out,         \
+                                             size_t rows, size_t n, size_t group, void *stream) {                                     \
+        if (op != PFHE_OP_MUL && op != PFHE_OP_ADD_MUL && op != PFHE_OP_SUB_MUL) return PFHE_ERR_INVALID_ARG;                         \
+        if (group == 0 || rows % group) return PFHE_ERR_INVALID_ARG;                                                                  \
+        if (rows * n == 0) return PFHE_OK;                                                                                            \
+        if (!a || !b || !out) return PFHE_ERR_INVALID_ARG;                                                                            \
+        LimbConsts<T> lc;                                                                                                             \
+        pfhe_status st = make_limb_consts<T>(moduli, limbs, nullptr, (int)op, lc);                                                    \
+        if (st != PFHE_OK) return st;                                                                                                 \
+        PFHE_CUDA(launch_slice_op<T>((int)op, lc, (int)limbs, a, b, nullptr, out, rows, n, static_cast<cudaStream_t>(stream), group)); \
+        return PFHE_OK;                                                                                                               \
+    }                                                                                                                                 \
     pfhe_status pfhe_mod##B##_butterfly_mul_factor(const T *moduli, size_t limbs, T *a, const T *s, const T *w, T *out, size_t rows,    \
                                                    size_t n, void *stream) {                                                          \
         LimbConsts<T> lc;                                                                                                             \

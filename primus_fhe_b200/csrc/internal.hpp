@@ -49,7 +49,7 @@ template <typename T> struct LimbConsts {
 };
 template <typename T>
 cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out,
-                            size_t rows, size_t n, cudaStream_t stream);
+                            size_t rows, size_t n, cudaStream_t stream, size_t b_group = 1);
 template <typename T>
 cudaError_t launch_butterfly_mul(const LimbConsts<T> &lc, int limbs, T *a, const T *s, const T *w, T *out, size_t rows, size_t n,
                                  cudaStream_t stream);

@@ -56,7 +56,9 @@ constexpr bool op_reads_out(int op) { return op == PFHE_OP_ADD_MUL || op == PFHE
 // slices are [rows][limbs][n]; vectorised when n % W == 0 (always true for polynomial lengths >= 4)
 template <typename T, int OP, bool VEC>
 __global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, const T *__restrict__ a,
-                                                       const T *__restrict__ b, const T *__restrict__ c, T *out, size_t rows, size_t n) {
+                                                       const T *__restrict__ b, const T *__restrict__ c, T *out, size_t rows, size_t n,
+                                                       size_t b_group) {
+    // b_group > 1: row r of `a` pairs with row r / b_group of `b` (one polynomial against every component of a ciphertext)
     constexpr int W = VEC ? VecOf<T>::W : 1;
     using V = typename VecOf<T>::type;
     const size_t per_row = n / W, total = rows * (size_t)limbs * per_row;
@@ -64,9 +66,14 @@ __global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ L
         const int limb = limbs == 1 ? 0 : (int)((gid / per_row) % (size_t)limbs);
         const Barrett<T> br = lc.br[limb];
         const T s = lc.scalar[limb], sq = lc.scalar_q[limb];
+        size_t bgid = gid;
+        if (op_reads_b(OP) && b_group > 1) {
+            const size_t row_len = (size_t)limbs * per_row, row = gid / row_len;
+            bgid = (row / b_group) * row_len + gid % row_len;
+        }
         if (VEC) {
             V va = reinterpret_cast<const V *>(a)[gid], vb, vc, vo;
-            if (op_reads_b(OP)) vb = reinterpret_cast<const V *>(b)[gid];
+            if (op_reads_b(OP)) vb = reinterpret_cast<const V *>(b)[bgid];
             if (op_reads_c(OP)) vc = reinterpret_cast<const V *>(c)[gid];
             if (op_reads_out(OP)) vo = reinterpret_cast<const V *>(out)[gid];
 #pragma unroll
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ L
                                           op_reads_out(OP) ? vo.v[k] : T(0));
             reinterpret_cast<V *>(out)[gid] = vo;
         } else {
-            out[gid] = apply_op<T, OP>(br, s, sq, a[gid], op_reads_b(OP) ? b[gid] : T(0), op_reads_c(OP) ? c[gid] : T(0),
+            out[gid] = apply_op<T, OP>(br, s, sq, a[gid], op_reads_b(OP) ? b[bgid] : T(0), op_reads_c(OP) ? c[gid] : T(0),
                                        op_reads_out(OP) ? out[gid] : T(0));
         }
     }
@@ -91,16 +98,16 @@ static unsigned stream_grid(size_t work_items, int threads) {
 
 template <typename T, int OP>
 static cudaError_t run_slice_op(const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out, size_t rows, size_t n,
-                                cudaStream_t stream) {
+                                size_t b_group, cudaStream_t stream) {
     constexpr int W = VecOf<T>::W;
     auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = (n % W == 0) && aligned(a) && aligned(out) && (!b || aligned(b)) && (!c || aligned(c));
     const size_t total = rows * (size_t)limbs * (vec ? n / W : n);
     if (total == 0) return cudaSuccess;
     if (vec)
-        slice_op_kernel<T, OP, true><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n);
+        slice_op_kernel<T, OP, true><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n, b_group);
     else
-        slice_op_kernel<T, OP, false><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n);
+        slice_op_kernel<T, OP, false><<<stream_grid(total, 256), 256, 0, stream>>>(lc, limbs, a, b, c, out, rows, n, b_group);
     count_launch();
     return cudaGetLastError();
 }
@@ -173,10 +180,10 @@ template cudaError_t launch_inv_slice<uint64_t>(const Barrett<uint64_t> &, const
 
 template <typename T>
 cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out, size_t rows, size_t n,
-                            cudaStream_t s) {
+                            cudaStream_t s, size_t b_group) {
     switch (op) {
 #define PFHE_CASE(OPC) \
-    case OPC: return run_slice_op<T, OPC>(lc, limbs, a, b, c, out, rows, n, s);
+    case OPC: return run_slice_op<T, OPC>(lc, limbs, a, b, c, out, rows, n, b_group, s);
         PFHE_CASE(PFHE_OP_MUL)
         PFHE_CASE(PFHE_OP_ADD_MUL)
         PFHE_CASE(PFHE_OP_SUB_MUL)
@@ -198,9 +205,9 @@ cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T 
     return cudaErrorInvalidValue;
 }
 template cudaError_t launch_slice_op<uint32_t>(int, const LimbConsts<uint32_t> &, int, const uint32_t *, const uint32_t *, const uint32_t *,
-                                               uint32_t *, size_t, size_t, cudaStream_t);
+                                               uint32_t *, size_t, size_t, cudaStream_t, size_t);
 template cudaError_t launch_slice_op<uint64_t>(int, const LimbConsts<uint64_t> &, int, const uint64_t *, const uint64_t *, const uint64_t *,
-                                               uint64_t *, size_t, size_t, cudaStream_t);
+                                               uint64_t *, size_t, size_t, cudaStream_t, size_t);
 
 // ---- gadget parameters (host) ---------------------------------------------------------------------
 template <typename T> bool make_gadget(T q, uint32_t log_basis, uint32_t levels_in, GadgetParams<T> &g) {

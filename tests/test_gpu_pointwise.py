@@ -232,3 +232,30 @@ def test_extract_lwe_variants_match_oracle(bits, q, n):
         P.extract_lwe_ex_batch(q, d, out, n, index=0, count=count, bits=bits)
         want = np.stack([O.extract_first_few_lwe(rlwe[b], count, q) for b in range(batch)])
         assert np.array_equal(out.cpu().numpy().view(dt), want)
+
+
+@pytest.mark.parametrize("bits,moduli,n,group", [(64, [1125899906826241], 1024, 2), (32, [132120577], 2048, 2),
+                                                 (64, [1125899906826241, 1125899906629633], 256, 3)])
+def test_ciphertext_times_polynomial_broadcast(bits, moduli, n, group):
+    """NttRlwe::mul_ntt_polynomial_to / add_ntt_rlwe_mul_ntt_polynomial_assign (primus_lattice/src/rlwe/ntt.rs:78-152): every
+    component of ciphertext i times polynomial i; checked against the oracle's per-polynomial Barrett slice ops."""
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    dt = np.uint64 if bits == 64 else np.uint32
+    rng = np.random.default_rng(19)
+    cts, L = 3, len(moduli)
+    mk = lambda r: np.stack([np.stack([rng.integers(0, m, n, dtype=np.uint64).astype(dt) for m in moduli]) for _ in range(r)])
+    a, b, acc = mk(cts * group), mk(cts), mk(cts * group)
+    want_mul, want_acc = np.empty_like(a), acc.copy()
+    for r in range(cts * group):
+        for li, m in enumerate(moduli):
+            om = O.BarrettModulus(m, bits)
+            want_mul[r, li] = om.reduce_mul_slice_to(a[r, li], b[r // group, li])
+            want_acc[r, li] = om.reduce_add_mul_slice_assign(want_acc[r, li].copy(), a[r, li], b[r // group, li])
+    out = torch.empty_like(_dev(a))
+    P.slice_op_bcast(P.api.OP_MUL, moduli, _dev(a), _dev(b), out, n, group, bits)
+    assert np.array_equal(out.cpu().numpy().view(dt).reshape(a.shape), want_mul)
+    dacc = _dev(acc.copy())
+    P.slice_op_bcast(P.api.OP_ADD_MUL, moduli, _dev(a), _dev(b), dacc, n, group, bits)
+    assert np.array_equal(dacc.cpu().numpy().view(dt).reshape(a.shape), want_acc)
