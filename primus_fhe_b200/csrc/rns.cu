@@ -101,35 +101,57 @@ __global__ void __launch_bounds__(128) rns_decompose_kernel(const __grid_constan
     }
 }
 
-// residues[limbs][count] -> digits[levels][limbs][count]: compose, init_value_carry, unsigned digits, centred lift
+// residues[limbs][count] -> digits[levels][limbs][count]: compose, init_value_carry, unsigned digits, centred lift.
+// One thread owns VEC consecutive coefficients so that every load / store is a 16-byte vector (the kernel is bound by
+// its levels*limbs stores per coefficient).
 template <typename T>
 __global__ void __launch_bounds__(128) rns_gadget_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
                                                          T *__restrict__ digits, size_t count, size_t polys, size_t in_stride,
                                                          size_t out_stride) {
     // `polys` independent CRT polynomials: residues + p*in_stride, digits + p*out_stride
-    constexpr int BITS = sizeof(T) * 8;
-    const size_t total = polys * count;
+    constexpr int BITS = sizeof(T) * 8, VEC = 16 / sizeof(T);
+    struct alignas(16) V {
+        T v[VEC];
+    };
+    const size_t cv = count / VEC, total = polys * cv;
+    const T bm1 = r.basis_m1, half = (T)((r.basis_m1 + 2) / 2);  // ceil(B/2)
     for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = gid / count, i = gid % count;
+        const size_t p = gid / cv, i = (gid % cv) * VEC;
         const T *res_in = residues + p * in_stride;
         T *dig = digits + p * out_stride;
-        T res[kRnsMaxLimbs], value[kRnsMaxWords + 1];
-        for (int l = 0; l < r.limbs; l++) res[l] = res_in[(size_t)l * count + i];
-        rns_compose<T>(r, res, value);
-        value[r.value_len] = 0;
-        if (r.has_threshold && big_ge<T>(value, r.threshold, r.value_len)) big_add<T>(value, r.add, r.value_len);
-        uint32_t carry = r.has_init_mask ? (uint32_t)((value[r.init_index] & r.init_mask) != 0) : 0u;
-        const T bm1 = r.basis_m1, half = (T)((r.basis_m1 + 2) / 2);  // ceil(B/2)
+        T value[VEC][kRnsMaxWords + 1];
+        uint32_t carry[VEC];
+        {
+            V in[kRnsMaxLimbs];
+            for (int l = 0; l < r.limbs; l++) in[l] = *reinterpret_cast<const V *>(res_in + (size_t)l * count + i);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                T res[kRnsMaxLimbs];
+                for (int l = 0; l < r.limbs; l++) res[l] = in[l].v[k];
+                rns_compose<T>(r, res, value[k]);
+                value[k][r.value_len] = 0;
+                if (r.has_threshold && big_ge<T>(value[k], r.threshold, r.value_len)) big_add<T>(value[k], r.add, r.value_len);
+                carry[k] = r.has_init_mask ? (uint32_t)((value[k][r.init_index] & r.init_mask) != 0) : 0u;
+            }
+        }
         for (uint32_t lv = 0; lv < r.levels; lv++) {
             const uint32_t pos = r.drop_bits + lv * r.log_basis;
             const int idx = pos / BITS, sh = pos % BITS;
-            T lower = value[idx] >> sh;
-            if (sh + (int)r.log_basis > BITS && idx + 1 < r.value_len) lower |= value[idx + 1] << (BITS - sh);
-            const T t = (lower & bm1) + carry;
-            carry = (t & r.carry_mask) != 0;
-            const T d = t & bm1;
-            for (int l = 0; l < r.limbs; l++)
-                dig[((size_t)lv * r.limbs + l) * count + i] = (r.basis_m1 == 1 || d < half) ? d : r.q[l] - (bm1 + 1) + d;
+            T d[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                T lower = value[k][idx] >> sh;
+                if (sh + (int)r.log_basis > BITS && idx + 1 < r.value_len) lower |= value[k][idx + 1] << (BITS - sh);
+                const T t = (lower & bm1) + carry[k];
+                carry[k] = (t & r.carry_mask) != 0;
+                d[k] = t & bm1;
+            }
+            for (int l = 0; l < r.limbs; l++) {
+                V o;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) o.v[k] = (r.basis_m1 == 1 || d[k] < half) ? d[k] : r.q[l] - (bm1 + 1) + d[k];
+                *reinterpret_cast<V *>(dig + ((size_t)lv * r.limbs + l) * count + i) = o;
+            }
         }
     }
 }
@@ -540,7 +562,10 @@ template <typename T>
 cudaError_t launch_rns_gadget(const RnsDev<T> &r, const T *residues, T *digits, size_t count, size_t polys, size_t in_stride, size_t out_stride,
                               cudaStream_t s) {
     if (!count || !polys) return cudaSuccess;
-    rns_gadget_kernel<T><<<grid_for(count * polys, 128), 128, 0, s>>>(r, residues, digits, count, polys, in_stride, out_stride);
+    if (count % (16 / sizeof(T)) || (in_stride % (16 / sizeof(T))) || (out_stride % (16 / sizeof(T))) || (reinterpret_cast<uintptr_t>(residues) & 15) ||
+        (reinterpret_cast<uintptr_t>(digits) & 15))
+        return cudaErrorNotSupported;  // polynomial lengths on this path are powers of two >= 4
+    rns_gadget_kernel<T><<<grid_for(count * polys / (16 / sizeof(T)), 128), 128, 0, s>>>(r, residues, digits, count, polys, in_stride, out_stride);
     count_launch();
     return cudaGetLastError();
 }
