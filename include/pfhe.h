@@ -291,6 +291,13 @@ pfhe_status pfhe_ggsw32_external_product_batch(const pfhe_ntt32 *t, uint32_t k, 
                                                const uint32_t *key, const uint32_t *in, uint32_t *out,
                                                size_t batch, int to_coeff, void *stream);
 
+/* Host-slice shim of the same product (HOST pointers; key uploaded once, ciphertexts pipelined H2D -> kernel -> D2H):
+ * the 1:1 forwarder for a Rust `mul_dcrt_ggsw_to` over host-resident ciphertexts. */
+pfhe_status pfhe_ggsw64_external_product_slices(const pfhe_ntt64 *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,
+                                                const uint64_t *key, const uint64_t *in, uint64_t *out, size_t batch, int to_coeff);
+pfhe_status pfhe_ggsw32_external_product_slices(const pfhe_ntt32 *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,
+                                                const uint32_t *key, const uint32_t *in, uint32_t *out, size_t batch, int to_coeff);
+
 /* Blind rotation composed from the reference's primitives (the reference has
  * no blind rotation: mul_monomial_assign primus_poly/src/poly/mul.rs:74-99, external product as
  * above, RLWE add).  bsk: device [n_lwe][2][levels][2][N] NTT domain; lwe: device

@@ -206,6 +206,16 @@ class _NttTable:
         check(f(self._h, k, log_basis, levels or 0, _dev_ptr(key, self.bits), _dev_ptr(glwe_in, self.bits),
                 _dev_ptr(out, self.bits, glwe_in.numel()), batch, int(to_coeff), _stream()))
 
+    def external_product_slices(self, k, log_basis, levels, key, glwe_in, out, to_coeff=True):
+        """Host-slice form of external_product_batch (numpy / CPU tensors)."""
+        f = getattr(lib(), f"pfhe_ggsw{self.bits}_external_product_slices")
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        size = glwe_in.numel() if _is_torch(glwe_in) else glwe_in.size
+        batch = size // ((k + 1) * self.n)
+        check(f(self._h, k, log_basis, levels or 0, _host_ptr(key, self.bits), _host_ptr(glwe_in, self.bits), _host_ptr(out, self.bits, size),
+                batch, int(bool(to_coeff))))
+        return out
+
     def blind_rotate_batch(self, log_basis, levels, bsk, n_lwe, lwe, test_vector, acc_out):
         """Composed blind rotation."""
         f = getattr(lib(), f"pfhe_blind_rotate{self.bits}_batch")

@@ -535,6 +535,37 @@ static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t
     PFHE_CUDA(launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
+// Host-slice shim of the single-modulus external product: key uploaded once, ciphertexts streamed through the pipelined
+// H2D -> kernel -> D2H path (the reference's CrtGlwe::mul_dcrt_ggsw_to works on host slices, primus_data/src/traits.rs:20).
+template <typename T, typename H>
+static pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,
+                                 int to_coeff) {
+    if (!t || ((!key || !in || !out) && batch)) return PFHE_ERR_INVALID_ARG;
+    GadgetParams<T> g;
+    if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
+    if (t->dev_lat.loge == 0 || k < 1 || k > 2) return PFHE_ERR_UNSUPPORTED;
+    if (batch == 0) return PFHE_OK;
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    cudaStream_t st[kPipe];
+    PFHE_CUDA(t_streams.get(t->device, st));
+    const size_t n = t->h.n, comps = (size_t)k + 1;
+    const size_t key_bytes = comps * g.levels * comps * n * sizeof(T), ct_bytes = comps * n * sizeof(T);
+    void *dkey = nullptr;
+    PFHE_CUDA(cudaMalloc(&dkey, key_bytes));
+    cudaError_t e = cudaMemcpy(dkey, key, key_bytes, cudaMemcpyHostToDevice);
+    pfhe_status status = e == cudaSuccess ? PFHE_OK : cuda_fail(e);
+    if (status == PFHE_OK) {
+        const void *ins[1] = {in};
+        const size_t inb[1] = {ct_bytes};
+        status = pipelined(t->device, ins, 1, inb, out, ct_bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
+            return launch_external_product<T>(t->dev_lat, g, k, static_cast<const T *>(dkey), static_cast<const T *>(din[0]),
+                                              static_cast<T *>(dout), nu, to_coeff != 0, s);
+        });
+    }
+    cudaFree(dkey);
+    return status;
+}
 template <typename T, typename H>
 static pfhe_status blind_rot(const H *t, uint32_t log_basis, uint32_t levels_in, const T *bsk, uint32_t n_lwe, const uint32_t *lwe,
                              const T *tv, T *acc_out, size_t batch, void *stream) {
@@ -826,6 +857,10 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     pfhe_status pfhe_ggsw##B##_external_product_batch(const pfhe_ntt##B *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,       \
                                                       const T *key, const T *in, T *out, size_t batch, int to_coeff, void *stream) {  \
         return ext_prod<T>(t, k, log_basis, levels_in, key, in, out, batch, to_coeff, stream);                                        \
+    }                                                                                                                                 \
+    pfhe_status pfhe_ggsw##B##_external_product_slices(const pfhe_ntt##B *t, uint32_t k, uint32_t log_basis, uint32_t levels_in,      \
+                                                       const T *key, const T *in, T *out, size_t batch, int to_coeff) {               \
+        return ext_prod_host<T>(t, k, log_basis, levels_in, key, in, out, batch, to_coeff);                                           \
     }                                                                                                                                 \
     pfhe_status pfhe_blind_rotate##B##_batch(const pfhe_ntt##B *t, uint32_t log_basis, uint32_t levels_in, const T *bsk,              \
                                              uint32_t n_lwe, const uint32_t *lwe, const T *test_vector, T *acc_out, size_t batch,     \

@@ -69,3 +69,22 @@ def test_blind_rotate_matches_oracle(bits, q, log_n, log_basis, n_lwe):
     out = torch.empty((batch, 2 * n), dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
     gt.blind_rotate_batch(log_basis, None, _dev(bsk), n_lwe, _dev(lwe), _dev(tv), out)
     assert np.array_equal(out.cpu().numpy().view(dt), want)
+
+
+def test_external_product_host_slices_match_device():
+    """pfhe_ggsw*_external_product_slices: host buffers in, host buffers out (what a host-resident `mul_dcrt_ggsw_to` binds to)."""
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    for bits, q in ((32, Q27), (64, Q50)):
+        dt = np.uint64 if bits == 64 else np.uint32
+        n, k = 1024, 1
+        gt = (P.U64NttTable if bits == 64 else P.U32NttTable)(10, q)
+        ot = (O.U64NttTable if bits == 64 else O.U32NttTable)(10, q)
+        ob = O.ApproxSignedBasis(q, 7, None, bits); levels = ob.decompose_length()
+        rng = np.random.default_rng(5)
+        key = rng.integers(0, q, 2 * levels * 2 * n, dtype=np.uint64).astype(dt)
+        cin = rng.integers(0, q, (7, 2 * n), dtype=np.uint64).astype(dt)
+        want = O.external_product_single(ot, ob, k, key, cin, to_coeff=True, batch=7)
+        out = np.empty_like(cin)
+        gt.external_product_slices(k, 7, None, key, cin, out, True)
+        assert np.array_equal(out, want)
