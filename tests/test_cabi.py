@@ -68,3 +68,35 @@ def test_multiply_factor_matches_reference_tests():
         P.MultiplyFactor(5, 40, 17)          # "Unsupported BitShift"
     with pytest.raises(P.PfheError):
         P.MultiplyFactor(17, 64, 17)         # operand must be less than modulus
+
+
+def test_host_only_handles_match_oracle_without_gpu():
+    """RNSBase / BigUintApproxSignedBasis geometry / BaseConverter handles are host-only value types (constants travel as
+    kernel parameters): constructors, error variants and geometry work -- and agree with the oracle -- on a CPU-only host."""
+    import pytest
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    with pytest.raises(P.PfheError) as e:
+        P.RNSBase([])
+    assert e.value.name == "EmptyBase"                                  # primus_rns/tests/rns.rs:67-70
+    with pytest.raises(P.PfheError) as e:
+        P.RNSBase([21, 35])
+    assert e.value.name == "CoPrimeError"                               # rns.rs:74-77
+    q50, q50b, q49 = 1125899906826241, 1125899906629633, 562949953392641
+    for bits, moduli in ((64, [3, 5, 7]), (64, [q50, q50b]), (64, [q50, q50b, q49]), (32, [134215681, 134176769])):
+        g, o = P.RNSBase(moduli, bits), O.RNSBase(moduli, bits)
+        assert g.big_uint_value_len() == o.big_uint_value_len() and g.moduli_product() == o.moduli_product()
+        for beta, rev in ((7, None), (1, None), (13, 2)):
+            if bits == 64 and moduli == [3, 5, 7] and beta > 6:
+                continue
+            gb, ob = P.BigUintApproxSignedBasis(g, beta, rev), O.BigUintApproxSignedBasis(o, beta, rev)
+            assert (gb.decompose_length(), gb.drop_bits()) == (ob.decompose_length(), ob.drop_bits())
+    with pytest.raises(P.PfheError):
+        P.BigUintApproxSignedBasis(P.RNSBase([q50, q50b]), 7, 99)        # more levels than the modulus has
+    P.BaseConverter([17, 19, 23], [29, 31])                             # rns.rs:282-284
+    with pytest.raises(P.PfheError) as e:
+        P.BaseConverter([17, 19, 23], [29, 58])
+    assert e.value.name == "CoPrimeError"
+    with pytest.raises(P.PfheError) as e:
+        P.BaseConverter([], [29])
+    assert e.value.name == "EmptyBase"
