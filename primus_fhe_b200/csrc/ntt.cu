@@ -58,6 +58,12 @@ struct SyncBlock {
 struct SyncWarp {
     __device__ __forceinline__ void operator()() const { __syncwarp(); }
 };
+// thread group of one polynomial inside a CTA that carries several: named barrier (id 1 + group), so that the groups do
+// not wait for each other at every exchange
+template <int TPP> struct SyncGroup {
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPP) : "memory"); }
+};
 template <int TPP> struct SyncFor {
     using type = SyncBlock;
 };
@@ -200,7 +206,9 @@ ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     const DevNtt<T> &tb = MULTI ? tb_limb : tb0;
     const typename F::Ctx c = F::ctx(tb);
     const uint32_t row = (uint32_t)(poly * Core::kTmaRows);
-    typename SyncFor<TPP>::type sync;
+    using SyncT = typename std::conditional<(PPB > 1 && TPP > 32), SyncGroup<TPP>, typename SyncFor<TPP>::type>::type;
+    SyncT sync;
+    if constexpr (PPB > 1 && TPP > 32) sync.id = 1 + grp;
     Elem x[E];
     if (FWD) {
         // input: strided coalesced LDG (a bulk-TMA copy-in measured no faster); output: one tensor store
