@@ -327,6 +327,10 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": "ntt_tma_kernel<F64LazyField,N=4096> forward (lazy-fold FP64 butterflies, TMA tensor store)", "algorithmic_bytes_per_launch": batch * BYTES_PER_NTT,
                 "avg_launch_ms": avg_kernel_ms,
+                "best_launch_ms": min(kernel_ms), "frac_best_launch": batch * BYTES_PER_NTT / (min(kernel_ms) * 1e-3) / 1e9 / peak,
+                "note": "achieved/frac use the AVERAGE launch over the timed region (the board reaches its power cap after ~0.1 s of this "
+                        "FP64-heavy kernel: see clocks.sm_mhz / reasons); peak is the burst copy bandwidth; best_launch is the fastest "
+                        "single launch of the same region",
                 "modmul": {"butterflies_per_s": batch * MODMULS_PER_NTT / (avg_kernel_ms * 1e-3),
                            "fp64_instr_per_ntt": FP64_PER_NTT, "fp64_pipe_peak_instr_per_s": FP64_PEAK,
                            "frac_of_fp64_pipe": batch * FP64_PER_NTT / (avg_kernel_ms * 1e-3) / FP64_PEAK,
