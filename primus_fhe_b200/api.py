@@ -269,18 +269,19 @@ class _DcrtTable:
     def moduli_count(self): return self._size("moduli_count")
     def crt_poly_length(self): return self._size("crt_poly_length")
 
-    def _hostn(self, name, polys):
+    def _hostn(self, name, polys, lazy=0):
         size = polys.numel() if _is_torch(polys) else polys.size
         unit = self.n * len(self.moduli)
         if size % unit:
             raise ValueError("buffer is not a multiple of the CRT polynomial length")
         f = getattr(lib(), self._p + name); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
-        check(f(self._h, _host_ptr(polys, self.bits), size // unit, 0))
+        check(f(self._h, _host_ptr(polys, self.bits), size // unit, int(lazy)))
 
     def transform_slice(self, poly): self._hostn("transform_slices", poly)
     def inverse_transform_slice(self, poly): self._hostn("inverse_transform_slices", poly)
-    lazy_transform_slice = transform_slice
-    lazy_inverse_transform_slice = inverse_transform_slice
+    # lazy trait contract (primus_ntt/src/dcrt/mod.rs:77-103): inputs in [0,4q_i) / [0,2q_i); outputs canonical (congruent, in range)
+    def lazy_transform_slice(self, poly): self._hostn("transform_slices", poly, 1)
+    def lazy_inverse_transform_slice(self, poly): self._hostn("inverse_transform_slices", poly, 1)
 
     def _batch(self, name, dev):
         unit = self.n * len(self.moduli)

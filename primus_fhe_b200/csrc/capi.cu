@@ -9,79 +9,13 @@
 #include <string>
 #include <vector>
 
-#include "host_math.hpp"
-#include "internal.hpp"
-#include "pfhe.h"
+#include "handles.hpp"
 #include "rns.hpp"
 
 namespace pfhe {
-int lattice_loge(int bits, int log_n);
 
-static thread_local std::string t_last_cuda_error;
-static pfhe_status cuda_fail(cudaError_t e) {
-    t_last_cuda_error = cudaGetErrorString(e);
-    cudaGetLastError();  // clear sticky-free errors
-    if (e == cudaErrorNotSupported) return PFHE_ERR_UNSUPPORTED;
-    return PFHE_ERR_CUDA;
-}
-#define PFHE_CUDA(expr)                                    \
-    do {                                                   \
-        cudaError_t _e = (expr);                           \
-        if (_e != cudaSuccess) return pfhe::cuda_fail(_e); \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) return;
-        ok = prev == dev || cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (ok && prev >= 0) {
-            int cur = -1;
-            cudaGetDevice(&cur);
-            if (cur != prev) cudaSetDevice(prev);
-        }
-    }
-};
-
-// per-thread copy streams (thread safe by construction)
-constexpr int kPipe = 4;  // pipeline depth of the host-slice shims (H2D / kernel / D2H + one slack stage)
-struct ThreadStreams {
-    std::vector<std::vector<cudaStream_t>> per_device;
-    cudaError_t get(int device, cudaStream_t *out) {
-        if ((int)per_device.size() <= device) per_device.resize(device + 1);
-        auto &v = per_device[device];
-        if (v.empty()) {
-            // keep freed staging buffers in the stream-ordered pool instead of returning them to the driver at every sync
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                uint64_t keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            v.resize(kPipe);
-            for (auto &s : v) {
-                cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-                if (e != cudaSuccess) {
-                    v.clear();
-                    return e;
-                }
-            }
-        }
-        for (int i = 0; i < kPipe; i++) out[i] = v[i];
-        return cudaSuccess;
-    }
-};
-static thread_local ThreadStreams t_streams;
-
-template <typename T> struct NttHandle {
-    int device = 0;
-    host::HostTables<T> h;
-    DevNtt<T> dev{};      // register-pass layout for the standalone NTT kernels
-    DevNtt<T> dev_lat{};  // same table, per-pass layout for the lattice kernels (loge == 0: unsupported size)
-    void *blob = nullptr;
-};
+thread_local std::string t_last_cuda_error;
+thread_local ThreadStreams t_streams;
 
 template <typename T>
 static void fill_pass_tables(const host::HostTables<T> &h, int loge, std::vector<typename Word<T>::Pair> &fwd,
@@ -152,6 +86,10 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     }
     inv[n - 1].x = h.inv_n_w;
     inv[n - 1].y = h.inv_n_w_q;
+    for (size_t k = 0; k < 8 && n >= 8; k++) {
+        hd->head.fwd_head[k] = fwd[k];
+        hd->head.inv_tail[k] = inv[n - 8 + k];
+    }
     const int loge = choose_loge(BITS, (int)log_n), loge_lat = lattice_loge(BITS, (int)log_n);
     if (loge) fill_pass_tables<T>(h, loge, fp, ip);
     if (loge_lat) fill_pass_tables<T>(h, loge_lat, fpl, ipl);
@@ -242,81 +180,6 @@ template <typename H> static void destroy_handle(H *h) {
     DeviceGuard guard(h->device);
     if (h->blob) cudaFree(h->blob);
     delete h;
-}
-
-template <typename T> struct DcrtHandle {
-    int device = 0;
-    std::vector<NttHandle<T> *> limbs;
-    DevNtt<T> *d_tables = nullptr;  // device array of the limb tables
-    DevNtt<T> *d_tables_lat = nullptr;  // same limbs, lattice-kernel pass layout (nullptr: unsupported degree)
-    int lat_policy = 0;                 // field policy of the fused multi-limb external product (internal.hpp)
-    DevNtt<T> tb0{};                // limb 0 by value (same field-policy flag as the device array)
-};
-
-// Pipelined host <-> device processing of `units` independent work items (`in_bytes`/`out_bytes` each).
-// launch(dev_in_chunks[], dev_out, n_units, stream).
-template <typename LaunchF>
-static pfhe_status pipelined(int device, const void *const *host_in, int n_in, const size_t *in_bytes, void *host_out, size_t out_bytes,
-                             size_t units, LaunchF launch, int out_alias = -1) {
-    if (units == 0) return PFHE_OK;
-    DeviceGuard guard(device);
-    if (!guard.ok) return PFHE_ERR_CUDA;
-    cudaStream_t st[kPipe];
-    PFHE_CUDA(t_streams.get(device, st));
-    size_t per_unit = out_alias >= 0 ? 0 : out_bytes;  // out_alias: the kernel updates input region #out_alias in place
-    for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];
-    // chunk so that each stage moves ~64 MiB (measured best on PCIe Gen5; PFHE_PIPE_CHUNK_MB overrides); at least one unit
-    size_t chunk_bytes = (size_t)64 << 20;
-    if (const char *e = getenv("PFHE_PIPE_CHUNK_MB")) {
-        const long mb = atol(e);
-        if (mb > 0 && mb <= 1024) chunk_bytes = (size_t)mb << 20;
-    }
-    size_t chunk = chunk_bytes / (per_unit ? per_unit : 1);
-    if (chunk == 0) chunk = 1;
-    if (chunk > units) chunk = units;
-    const int nbuf = (int)((units + chunk - 1) / chunk < (size_t)kPipe ? (units + chunk - 1) / chunk : kPipe);
-    void *dbuf[kPipe] = {};
-    pfhe_status status = PFHE_OK;
-    for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaMallocAsync(&dbuf[i], chunk * per_unit, st[i]);
-        if (e != cudaSuccess) {
-            status = cuda_fail(e);
-            break;
-        }
-    }
-    if (status == PFHE_OK) {
-        size_t done = 0;
-        for (int c = 0; done < units; c++) {
-            const int b = c % nbuf;
-            const size_t nu = units - done < chunk ? units - done : chunk;
-            unsigned char *base = static_cast<unsigned char *>(dbuf[b]);
-            const void *din[4] = {nullptr, nullptr, nullptr, nullptr};
-            size_t off = 0;
-            cudaError_t e = cudaSuccess;
-            for (int i = 0; i < n_in && e == cudaSuccess; i++) {
-                din[i] = base + off;
-                e = cudaMemcpyAsync(base + off, static_cast<const unsigned char *>(host_in[i]) + done * in_bytes[i], nu * in_bytes[i],
-                                    cudaMemcpyHostToDevice, st[b]);
-                off += chunk * in_bytes[i];
-            }
-            void *dout = out_alias >= 0 ? const_cast<void *>(din[out_alias]) : static_cast<void *>(base + off);
-            if (e == cudaSuccess) e = launch(din, dout, nu, st[b]);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(static_cast<unsigned char *>(host_out) + done * out_bytes, dout, nu * out_bytes, cudaMemcpyDeviceToHost,
-                                    st[b]);
-            if (e != cudaSuccess) {
-                status = cuda_fail(e);
-                break;
-            }
-            done += nu;
-        }
-    }
-    for (int i = 0; i < nbuf; i++) {
-        if (dbuf[i]) cudaFreeAsync(dbuf[i], st[i]);
-        cudaError_t e = cudaStreamSynchronize(st[i]);
-        if (e != cudaSuccess && status == PFHE_OK) status = cuda_fail(e);
-    }
-    return status;
 }
 
 template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd, bool lazy = false) {
@@ -410,10 +273,6 @@ static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *
 
 using namespace pfhe;
 
-struct pfhe_ntt32 : NttHandle<uint32_t> {};
-struct pfhe_ntt64 : NttHandle<uint64_t> {};
-struct pfhe_dcrt32 : DcrtHandle<uint32_t> {};
-struct pfhe_dcrt64 : DcrtHandle<uint64_t> {};
 template <typename T> struct RnsHandle {
     std::vector<T> moduli;
     RnsDev<T> base{};  // RNS part only (log_basis = 0); gadget variants are derived per call (a few hundred host cycles)
@@ -483,13 +342,20 @@ static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size
     return PFHE_OK;
 }
 
-template <typename T, typename D> static pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd) {
+template <typename T, typename D> static pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd, bool lazy) {
     if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
     const size_t L = t->limbs.size();
     const size_t bytes = (sizeof(T) << t->limbs[0]->h.log_n) * L;
     const void *ins[1] = {polys};
     const size_t inb[1] = {bytes};
+    LimbConsts<T> lc{};
+    for (size_t i = 0; i < L; i++) lc.br[i] = t->limbs[i]->dev.br;
     return pipelined(t->device, ins, 1, inb, polys, bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
+        if (lazy) {  // lazy trait contract (dcrt/mod.rs:77-103): inputs in [0,4q_i) / [0,2q_i) -> canonicalise per limb on the device first
+            T *src = const_cast<T *>(static_cast<const T *>(din[0]));
+            cudaError_t e = launch_slice_op<T>(PFHE_OP_REDUCE_LAZY, lc, (int)L, src, nullptr, nullptr, src, nu, (size_t)1 << t->limbs[0]->h.log_n, s);
+            if (e != cudaSuccess) return e;
+        }
         return launch_ntt<T>(t->tb0, t->d_tables, (int)L, static_cast<const T *>(din[0]), static_cast<T *>(dout), nu * L, fwd, s);
     });
 }
@@ -574,6 +440,14 @@ static pfhe_status blind_rot(const H *t, uint32_t log_basis, uint32_t levels_in,
     if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
     if (t->dev_lat.loge == 0) return PFHE_ERR_UNSUPPORTED;
     DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    if constexpr (sizeof(T) == 4) {  // bootstrapping shape of BASELINE config 5: the re-scheduled kernel of lattice32.cu
+        const cudaError_t e = launch_blind_rotate_fast32(t->dev_lat, t->head, g, bsk, n_lwe, lwe, tv, acc_out, batch, static_cast<cudaStream_t>(stream));
+        if (e != cudaErrorNotSupported) {
+            PFHE_CUDA(e);
+            return PFHE_OK;
+        }
+    }
     PFHE_CUDA(launch_blind_rotate<T>(t->dev_lat, g, bsk, n_lwe, lwe, tv, acc_out, batch, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
@@ -765,11 +639,11 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     const pfhe_ntt##B *pfhe_dcrt##B##_ntt_table(const pfhe_dcrt##B *t, size_t limb) {                                                 \
         return (t && limb < t->limbs.size()) ? static_cast<const pfhe_ntt##B *>(t->limbs[limb]) : nullptr;                            \
     }                                                                                                                                 \
-    pfhe_status pfhe_dcrt##B##_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int) {                                     \
-        return dcrt_host_transform<T>(t, p, batch, true);                                                                             \
+    pfhe_status pfhe_dcrt##B##_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int lazy) {                                \
+        return dcrt_host_transform<T>(t, p, batch, true, lazy != 0);                                                                  \
     }                                                                                                                                 \
-    pfhe_status pfhe_dcrt##B##_inverse_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int) {                             \
-        return dcrt_host_transform<T>(t, p, batch, false);                                                                            \
+    pfhe_status pfhe_dcrt##B##_inverse_transform_slices(const pfhe_dcrt##B *t, T *p, size_t batch, int lazy) {                        \
+        return dcrt_host_transform<T>(t, p, batch, false, lazy != 0);                                                                 \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_forward_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \

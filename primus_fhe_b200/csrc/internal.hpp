@@ -63,7 +63,16 @@ cudaError_t launch_rns_lift(const T *moduli_host, int limbs, T small_modulus, co
 template <typename T>
 cudaError_t launch_extract_lwe(T q, const T *rlwe, T *lwe, size_t n, size_t batch, size_t index, size_t count, cudaStream_t stream);
 
-// ---- lattice (lattice.cu) ---------------------------------------------------------------------
+// ---- lattice (lattice.cu, lattice32.cu) -----------------------------------------------------------
+// Host copy of the table entries the fast lattice kernels read from the kernel-parameter bank:
+// fwd[0..7] (forward stages 0..2) and inv[N-8..N-1] (last three inverse stages; entry 7 = n^-1 * inv_roots[N-1]).
+template <typename T> struct LatHead {
+    typename Word<T>::Pair fwd_head[8], inv_tail[8];
+};
+// u32, N = 1024 bootstrapping shape (lattice32.cu); cudaErrorNotSupported when (table, gadget) does not qualify
+cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
+                                       const uint32_t *bsk, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
+                                       uint32_t *acc_out, size_t batch, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_external_product(const DevNtt<T> &tb, const GadgetParams<T> &g, uint32_t k, const T *key, const T *in,
                                     T *out, size_t batch, bool to_coeff, cudaStream_t stream);
