@@ -410,6 +410,170 @@ pfhe_status pfhe_mod64_dot_product_batch(uint64_t q, const uint64_t *a, const ui
 pfhe_status pfhe_mod32_dot_product_batch(uint32_t q, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t rows, size_t n, void *stream);
 
 /* ===================================================================================== */
+/* Bootstrapping keys and the host-slice bootstrap (round 2)                               */
+/* ===================================================================================== */
+/* A bootstrapping key = n_lwe RGSW ciphertexts in NTT form, [n_lwe][2][levels][2][N] words (NttRgsw layout,
+ * primus_lattice/src/ggsw/dcrt.rs:14-31 with L = 1), uploaded once to the table's device and kept resident like a table
+ * (the reference keeps keys in host `Vec`s; a GPU caller holds this handle instead).  `bsk` is HOST memory.
+ * `_create_from_bytes` takes the reference's serialised form (`to_bytes`, raw little-endian words, macros/mod.rs:39-97). */
+typedef struct pfhe_bsk32 pfhe_bsk32;
+typedef struct pfhe_bsk64 pfhe_bsk64;
+pfhe_status pfhe_bsk64_create(const pfhe_ntt64 *t, uint32_t log_basis, uint32_t levels_in, uint32_t n_lwe, const uint64_t *bsk, pfhe_bsk64 **out);
+pfhe_status pfhe_bsk32_create(const pfhe_ntt32 *t, uint32_t log_basis, uint32_t levels_in, uint32_t n_lwe, const uint32_t *bsk, pfhe_bsk32 **out);
+pfhe_status pfhe_bsk64_create_from_bytes(const pfhe_ntt64 *t, uint32_t log_basis, uint32_t levels_in, uint32_t n_lwe, const uint8_t *bytes,
+                                         size_t byte_count, pfhe_bsk64 **out);
+pfhe_status pfhe_bsk32_create_from_bytes(const pfhe_ntt32 *t, uint32_t log_basis, uint32_t levels_in, uint32_t n_lwe, const uint8_t *bytes,
+                                         size_t byte_count, pfhe_bsk32 **out);
+void pfhe_bsk64_destroy(pfhe_bsk64 *b);
+void pfhe_bsk32_destroy(pfhe_bsk32 *b);
+uint32_t pfhe_bsk64_lwe_dimension(const pfhe_bsk64 *b);
+uint32_t pfhe_bsk32_lwe_dimension(const pfhe_bsk32 *b);
+uint32_t pfhe_bsk64_levels(const pfhe_bsk64 *b);
+uint32_t pfhe_bsk32_levels(const pfhe_bsk32 *b);
+const uint64_t *pfhe_bsk64_device_ptr(const pfhe_bsk64 *b); /* device pointer for the *_batch entry points */
+const uint32_t *pfhe_bsk32_device_ptr(const pfhe_bsk32 *b);
+/* Bootstrap on HOST slices: lwe [batch][n_lwe+1] uint32 in Z_2N (a_0..a_{n-1}, b), test_vector [N];
+ * extract != 0: out [batch][N+1] = Rlwe::extract_lwe (rlwe/coeff.rs:264-288) of the rotated accumulator;
+ * extract == 0: out [batch][2][N] = the accumulator itself.  H2D -> blind rotation -> D2H inside the call. */
+pfhe_status pfhe_bootstrap64_slices(const pfhe_ntt64 *t, const pfhe_bsk64 *bsk, const uint32_t *lwe, const uint64_t *test_vector,
+                                    uint64_t *out, size_t batch, int extract);
+pfhe_status pfhe_bootstrap32_slices(const pfhe_ntt32 *t, const pfhe_bsk32 *bsk, const uint32_t *lwe, const uint32_t *test_vector,
+                                    uint32_t *out, size_t batch, int extract);
+/* LWE modulus switch to Z_2N before blind rotation (NOT in the reference -- it has no bootstrapping; convention fixed here and
+ * in the oracle): out[i] = floor((lwe[i] * 2N + floor(q/2)) / q) mod 2N, exact integer arithmetic; 2N = 2^log_2n.
+ * lwe: device, `count` canonical words (all a_i and b of a batch); out: device uint32. */
+pfhe_status pfhe_lwe64_modulus_switch_batch(uint64_t q, uint32_t log_2n, const uint64_t *lwe, uint32_t *out, size_t count, void *stream);
+pfhe_status pfhe_lwe32_modulus_switch_batch(uint32_t q, uint32_t log_2n, const uint32_t *lwe, uint32_t *out, size_t count, void *stream);
+
+/* ===================================================================================== */
+/* Multi-device drivers (round 2): one process, several GPUs, no torch                     */
+/* ===================================================================================== */
+/* NttTable is Send + Sync (primus_ntt/src/ntt/mod.rs:16): the reference lets a caller fan a batch out over threads.  Here the
+ * fan-out is over devices: `tables[i]` is the same (log_n, q) table created on device i (pfhe_multi_ntt*_create replicates it),
+ * the batch is split into contiguous shards (sizes differ by at most one: shard r of `total` starts at
+ * r*floor(total/n) + min(r, total mod n)), one host thread with its own stream set drives each device, and the call returns
+ * when every shard is back in host memory.  No collective on the data path.  The same device may appear
+ * more than once (two handles on one GPU) -- the shards then overlap on that GPU. */
+pfhe_status pfhe_multi_ntt64_create(const int *devices, size_t n_devices, uint32_t log_n, uint64_t q, pfhe_ntt64 **out_tables);
+pfhe_status pfhe_multi_ntt32_create(const int *devices, size_t n_devices, uint32_t log_n, uint32_t q, pfhe_ntt32 **out_tables);
+pfhe_status pfhe_multi_ntt64_transform_slices(const pfhe_ntt64 *const *tables, size_t n_devices, uint64_t *polys, size_t batch, int inverse, int lazy);
+pfhe_status pfhe_multi_ntt32_transform_slices(const pfhe_ntt32 *const *tables, size_t n_devices, uint32_t *polys, size_t batch, int inverse, int lazy);
+pfhe_status pfhe_multi_ntt64_polymul_slices(const pfhe_ntt64 *const *tables, size_t n_devices, const uint64_t *a, const uint64_t *b, uint64_t *c, size_t batch);
+pfhe_status pfhe_multi_ntt32_polymul_slices(const pfhe_ntt32 *const *tables, size_t n_devices, const uint32_t *a, const uint32_t *b, uint32_t *c, size_t batch);
+pfhe_status pfhe_multi_ggsw64_external_product_slices(const pfhe_ntt64 *const *tables, size_t n_devices, uint32_t k, uint32_t log_basis,
+                                                      uint32_t levels_in, const uint64_t *key, const uint64_t *in, uint64_t *out, size_t batch, int to_coeff);
+pfhe_status pfhe_multi_ggsw32_external_product_slices(const pfhe_ntt32 *const *tables, size_t n_devices, uint32_t k, uint32_t log_basis,
+                                                      uint32_t levels_in, const uint32_t *key, const uint32_t *in, uint32_t *out, size_t batch, int to_coeff);
+pfhe_status pfhe_multi_bootstrap64_slices(const pfhe_ntt64 *const *tables, const pfhe_bsk64 *const *bsks, size_t n_devices, const uint32_t *lwe,
+                                          const uint64_t *test_vector, uint64_t *out, size_t batch, int extract);
+pfhe_status pfhe_multi_bootstrap32_slices(const pfhe_ntt32 *const *tables, const pfhe_bsk32 *const *bsks, size_t n_devices, const uint32_t *lwe,
+                                          const uint32_t *test_vector, uint32_t *out, size_t batch, int extract);
+
+/* ===================================================================================== */
+/* Whole-ciphertext transforms and the byte wire format (round 2)                          */
+/* ===================================================================================== */
+/* into_ntt_form / into_coeff_form / write_ntt_form / write_coeff_form of every ciphertext container
+ * (primus_lattice/src/macros/mod.rs:537-621 impl_ntt / impl_intt; CRT forms :623-674, :892-937): transform every polynomial of
+ * the flat HOST storage (`words` must be a multiple of N, resp. L*N) in one pipelined call.  `write_*` copies src to dst first,
+ * exactly like `result.0.copy_from_slice(self.as_ref())`. */
+pfhe_status pfhe_cipher64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, size_t words);
+pfhe_status pfhe_cipher32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, size_t words);
+pfhe_status pfhe_cipher64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, size_t words);
+pfhe_status pfhe_cipher32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, size_t words);
+pfhe_status pfhe_cipher64_write_ntt_form(const pfhe_ntt64 *t, const uint64_t *src, uint64_t *dst, size_t words);
+pfhe_status pfhe_cipher32_write_ntt_form(const pfhe_ntt32 *t, const uint32_t *src, uint32_t *dst, size_t words);
+pfhe_status pfhe_cipher64_write_coeff_form(const pfhe_ntt64 *t, const uint64_t *src, uint64_t *dst, size_t words);
+pfhe_status pfhe_cipher32_write_coeff_form(const pfhe_ntt32 *t, const uint32_t *src, uint32_t *dst, size_t words);
+pfhe_status pfhe_dcrt_cipher64_into_ntt_form(const pfhe_dcrt64 *t, uint64_t *data, size_t words);   /* CrtGlwe/CrtGlev/CrtGgsw -> Dcrt* */
+pfhe_status pfhe_dcrt_cipher32_into_ntt_form(const pfhe_dcrt32 *t, uint32_t *data, size_t words);
+pfhe_status pfhe_dcrt_cipher64_into_coeff_form(const pfhe_dcrt64 *t, uint64_t *data, size_t words); /* Dcrt* -> Crt* (macros/mod.rs:892-937) */
+pfhe_status pfhe_dcrt_cipher32_into_coeff_form(const pfhe_dcrt32 *t, uint32_t *data, size_t words);
+/* Named containers: word counts of the reference's flat layouts and the matching transforms.
+ * Rlwe [2][N] (rlwe/coeff.rs), Rlev [levels][2][N], Rgsw [2][levels][2][N], Glwe [k+1][N] (glwe/), Glev [levels][k+1][N],
+ * Ggsw [k+1][levels][k+1][N] (ggsw/dcrt.rs:14-31). */
+size_t pfhe_rlwe64_words(const pfhe_ntt64 *t);
+size_t pfhe_rlwe32_words(const pfhe_ntt32 *t);
+size_t pfhe_rlev64_words(const pfhe_ntt64 *t, uint32_t levels);
+size_t pfhe_rlev32_words(const pfhe_ntt32 *t, uint32_t levels);
+size_t pfhe_rgsw64_words(const pfhe_ntt64 *t, uint32_t levels);
+size_t pfhe_rgsw32_words(const pfhe_ntt32 *t, uint32_t levels);
+size_t pfhe_glwe64_words(const pfhe_ntt64 *t, uint32_t k);
+size_t pfhe_glwe32_words(const pfhe_ntt32 *t, uint32_t k);
+size_t pfhe_glev64_words(const pfhe_ntt64 *t, uint32_t k, uint32_t levels);
+size_t pfhe_glev32_words(const pfhe_ntt32 *t, uint32_t k, uint32_t levels);
+size_t pfhe_ggsw64_words(const pfhe_ntt64 *t, uint32_t k, uint32_t levels);
+size_t pfhe_ggsw32_words(const pfhe_ntt32 *t, uint32_t k, uint32_t levels);
+pfhe_status pfhe_rlwe64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data);
+pfhe_status pfhe_rlwe32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data);
+pfhe_status pfhe_rlwe64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data);
+pfhe_status pfhe_rlwe32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data);
+pfhe_status pfhe_rlev64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t levels);
+pfhe_status pfhe_rlev32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t levels);
+pfhe_status pfhe_rlev64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t levels);
+pfhe_status pfhe_rlev32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t levels);
+pfhe_status pfhe_rgsw64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t levels);
+pfhe_status pfhe_rgsw32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t levels);
+pfhe_status pfhe_rgsw64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t levels);
+pfhe_status pfhe_rgsw32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t levels);
+pfhe_status pfhe_glwe64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k);
+pfhe_status pfhe_glwe32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k);
+pfhe_status pfhe_glwe64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k);
+pfhe_status pfhe_glwe32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k);
+pfhe_status pfhe_glev64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_glev32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_glev64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_glev32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_ggsw64_into_ntt_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_ggsw32_into_ntt_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_ggsw64_into_coeff_form(const pfhe_ntt64 *t, uint64_t *data, uint32_t k, uint32_t levels);
+pfhe_status pfhe_ggsw32_into_coeff_form(const pfhe_ntt32 *t, uint32_t *data, uint32_t k, uint32_t levels);
+/* from_bytes / read_bytes / to_bytes / write_bytes / byte_count (macros/mod.rs:39-97: `bytemuck::cast_slice`, i.e. the raw
+ * little-endian bytes of the flat word array -- also the host<->device wire format, so a serialised key can be uploaded as is).
+ * Unlike bytemuck, unaligned byte buffers are accepted.  byte_count must equal word_count * sizeof(word). */
+pfhe_status pfhe_cipher64_read_bytes(uint64_t *words, size_t word_count, const uint8_t *bytes, size_t byte_count);
+pfhe_status pfhe_cipher32_read_bytes(uint32_t *words, size_t word_count, const uint8_t *bytes, size_t byte_count);
+pfhe_status pfhe_cipher64_write_bytes(const uint64_t *words, size_t word_count, uint8_t *bytes, size_t byte_count);
+pfhe_status pfhe_cipher32_write_bytes(const uint32_t *words, size_t word_count, uint8_t *bytes, size_t byte_count);
+size_t pfhe_cipher64_byte_count(size_t word_count);
+size_t pfhe_cipher32_byte_count(size_t word_count);
+
+/* ===================================================================================== */
+/* UintNttTable<T> (primus_ntt/src/ntt/primitive.rs:37-396) -- the generic table (round 2)   */
+/* ===================================================================================== */
+/* A distinct table type with the reference's constructor rules: NoPrimitiveRoot (root.rs:72-81), DegreeConversionErr when
+ * N does not fit the word type (primitive.rs:160-161), DegreeTooLarge when N >= q (:163-168); ModulusTooLarge when 4q does not
+ * fit the word (the lazy butterflies keep values in [0,4q), :219-236).  Words: u16 / u32 / u64 (FheUint,
+ * primus_integer/src/unsigned_integer.rs:27-112).  Always runs the plain radix-2 kernel (the reference's cross-check
+ * implementation: canonical results equal U32/U64NttTable, prime64/tests.rs:78-237). */
+typedef struct pfhe_uintntt16 pfhe_uintntt16;
+typedef struct pfhe_uintntt32 pfhe_uintntt32;
+typedef struct pfhe_uintntt64 pfhe_uintntt64;
+pfhe_status pfhe_uintntt16_create(int device, uint32_t log_n, uint16_t q, pfhe_uintntt16 **out);
+pfhe_status pfhe_uintntt32_create(int device, uint32_t log_n, uint32_t q, pfhe_uintntt32 **out);
+pfhe_status pfhe_uintntt64_create(int device, uint32_t log_n, uint64_t q, pfhe_uintntt64 **out);
+void pfhe_uintntt16_destroy(pfhe_uintntt16 *t);
+void pfhe_uintntt32_destroy(pfhe_uintntt32 *t);
+void pfhe_uintntt64_destroy(pfhe_uintntt64 *t);
+size_t pfhe_uintntt16_poly_length(const pfhe_uintntt16 *t);
+size_t pfhe_uintntt32_poly_length(const pfhe_uintntt32 *t);
+size_t pfhe_uintntt64_poly_length(const pfhe_uintntt64 *t);
+uint16_t pfhe_uintntt16_root(const pfhe_uintntt16 *t);
+uint32_t pfhe_uintntt32_root(const pfhe_uintntt32 *t);
+uint64_t pfhe_uintntt64_root(const pfhe_uintntt64 *t);
+uint16_t pfhe_uintntt16_inv_root(const pfhe_uintntt16 *t);
+uint32_t pfhe_uintntt32_inv_root(const pfhe_uintntt32 *t);
+uint64_t pfhe_uintntt64_inv_root(const pfhe_uintntt64 *t);
+/* the same table viewed through the NttTable entry points (monomial transforms, device batches) */
+const pfhe_ntt32 *pfhe_uintntt32_as_table(const pfhe_uintntt32 *t);
+const pfhe_ntt64 *pfhe_uintntt64_as_table(const pfhe_uintntt64 *t);
+pfhe_status pfhe_uintntt16_transform_slices(const pfhe_uintntt16 *t, uint16_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_uintntt32_transform_slices(const pfhe_uintntt32 *t, uint32_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_uintntt64_transform_slices(const pfhe_uintntt64 *t, uint64_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_uintntt16_inverse_transform_slices(const pfhe_uintntt16 *t, uint16_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_uintntt32_inverse_transform_slices(const pfhe_uintntt32 *t, uint32_t *polys, size_t batch, int lazy);
+pfhe_status pfhe_uintntt64_inverse_transform_slices(const pfhe_uintntt64 *t, uint64_t *polys, size_t batch, int lazy);
+
+/* ===================================================================================== */
 /* Plumbing for hosts without a CUDA binding of their own (the Rust FFI crate, tests)      */
 /* ===================================================================================== */
 pfhe_status pfhe_device_count(int *count);
@@ -421,7 +585,8 @@ pfhe_status pfhe_stream_synchronize(int device, void *stream);
 
 /* Integer-pipe microbenchmark used to measure the modmul roofline denominator
  * (SURVEY.md 8d): runs `iters` dependent Shoup modmuls per thread in registers on
- * `blocks` x 256 threads and returns elapsed milliseconds via *ms. kind: 0 = u32, 1 = u64. */
+ * `blocks` x 256 threads and returns elapsed milliseconds via *ms. kind: 0 = u32 Harvey butterflies, 1 = u64 Harvey
+ * butterflies, 2 = bare u32 Shoup products (1 high + 2 low multiplies), 3 = bare u64 Shoup products; 8 per thread per iteration. */
 pfhe_status pfhe_modmul_microbench(int device, int kind, uint32_t blocks, uint32_t iters, float *ms);
 
 #ifdef __cplusplus

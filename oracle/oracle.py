@@ -640,3 +640,11 @@ def blind_rotate(table: _NttTable, basis: ApproxSignedBasis, bsk, n_lwe, lwe, te
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
     f(table._h, C.byref(basis._s), _ptr(bsk), n_lwe, _ptr(lwe), _ptr(tv), _ptr(out), batch, threads or max_threads())
     return out
+
+
+def modulus_switch(lwe, q, log_2n):
+    """LWE modulus switch q -> 2N = 2^log_2n, round to nearest: floor((v * 2N + floor(q/2)) / q) mod 2N.
+    NOT in the reference (it has no bootstrapping); the convention is fixed here and in include/pfhe.h. Exact big-int arithmetic."""
+    two_n = 1 << log_2n
+    flat = [((int(v) * two_n + q // 2) // q) % two_n for v in np.asarray(lwe).reshape(-1)]
+    return np.array(flat, dtype=np.uint32).reshape(np.asarray(lwe).shape)

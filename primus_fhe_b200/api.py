@@ -645,3 +645,232 @@ def modmul_microbench(kind: int, blocks: int, iters: int, device: int = 0) -> fl
     f.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
     check(f(device, kind, blocks, iters, C.byref(ms)))
     return ms.value
+
+
+# ======================================================================================================
+# Round 2: bootstrapping keys, multi-device drivers, whole-ciphertext transforms, bytes, UintNttTable
+# ======================================================================================================
+def _size(x):
+    return x.numel() if _is_torch(x) else x.size
+
+
+class BootstrappingKey:
+    """n_lwe RGSW ciphertexts in NTT form, resident on the table's device (pfhe_bsk*_create).
+    `bsk`: host array [n_lwe][2][levels][2][N] (NttRgsw layout) or its `to_bytes()` image (bytes / bytearray / memoryview)."""
+
+    def __init__(self, table: _NttTable, log_basis, levels, n_lwe, bsk):
+        self.table, self.bits, self.n_lwe = table, table.bits, int(n_lwe)
+        self._h = C.c_void_p()
+        if isinstance(bsk, (bytes, bytearray, memoryview)):
+            buf = (C.c_char * len(bsk)).from_buffer_copy(bytes(bsk))
+            f = getattr(lib(), f"pfhe_bsk{self.bits}_create_from_bytes")
+            f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+            check(f(table._h, log_basis, levels or 0, n_lwe, buf, len(bsk), C.byref(self._h)))
+        else:
+            f = getattr(lib(), f"pfhe_bsk{self.bits}_create")
+            f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+            lv = ApproxSignedBasis(table.q, log_basis, levels, self.bits).decompose_length()
+            check(f(table._h, log_basis, levels or 0, n_lwe, _host_ptr(bsk, self.bits, n_lwe * 2 * lv * 2 * table.n), C.byref(self._h)))
+        g = getattr(lib(), f"pfhe_bsk{self.bits}_levels"); g.argtypes = [C.c_void_p]; g.restype = C.c_uint32
+        self.levels = int(g(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                f = getattr(lib(), f"pfhe_bsk{self.bits}_destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(self._h); self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def device_ptr(self) -> int:
+        f = getattr(lib(), f"pfhe_bsk{self.bits}_device_ptr"); f.argtypes = [C.c_void_p]; f.restype = C.c_void_p
+        return int(f(self._h) or 0)
+
+    def bootstrap_slices(self, lwe, test_vector, out=None, extract=True):
+        """Host LWE samples (uint32 [batch][n_lwe+1], already in Z_2N) -> host LWE [batch][N+1] (extract) or accumulators [batch][2][N]."""
+        t = self.table
+        batch = _size(lwe) // (self.n_lwe + 1)
+        width = (t.n + 1) if extract else 2 * t.n
+        if out is None:
+            out = np.empty((batch, width), dtype=_np_dtype(self.bits))
+        f = getattr(lib(), f"pfhe_bootstrap{self.bits}_slices")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(t._h, self._h, _host_ptr(lwe, 32, batch * (self.n_lwe + 1)), _host_ptr(test_vector, self.bits, t.n),
+                _host_ptr(out, self.bits, batch * width), batch, int(bool(extract))))
+        return out
+
+
+def modulus_switch_batch(q, log_2n, lwe, out, bits=64):
+    """LWE modulus switch q -> 2N = 2^log_2n (round to nearest; not in the reference): CUDA words in, CUDA uint32 out."""
+    f = getattr(lib(), f"pfhe_lwe{bits}_modulus_switch_batch")
+    f.argtypes = [_ct(bits), C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    check(f(int(q), int(log_2n), _dev_ptr(lwe, bits), _dev_ptr(out, 32, lwe.numel()), lwe.numel(), _stream()))
+
+
+class MultiNttTable:
+    """The same (log_n, q) table replicated on several devices of one process; host-slice calls are split into contiguous
+    shards, one host thread per device (pfhe_multi_*).  `devices` may repeat a device index."""
+
+    def __init__(self, log_n, modulus, devices, bits=64):
+        self.bits, self.devices = bits, list(devices)
+        cls = U64NttTable if bits == 64 else U32NttTable
+        self.tables = [cls(log_n, modulus, device=d) for d in self.devices]
+        self.n, self.q = self.tables[0].n, self.tables[0].q
+        self._arr = (C.c_void_p * len(self.tables))(*[t._h for t in self.tables])
+
+    def _p(self, name):
+        return getattr(lib(), name.replace("#", str(self.bits)))
+
+    def transform_slices(self, polys, inverse=False, lazy=False):
+        f = self._p("pfhe_multi_ntt#_transform_slices"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        check(f(self._arr, len(self.tables), _host_ptr(polys, self.bits), _size(polys) // self.n, int(inverse), int(lazy)))
+
+    def inverse_transform_slices(self, polys): self.transform_slices(polys, inverse=True)
+
+    def polymul_slices(self, a, b, c):
+        f = self._p("pfhe_multi_ntt#_polymul_slices"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        check(f(self._arr, len(self.tables), _host_ptr(a, self.bits), _host_ptr(b, self.bits, _size(a)), _host_ptr(c, self.bits, _size(a)),
+                _size(a) // self.n))
+        return c
+
+    def external_product_slices(self, k, log_basis, levels, key, glwe_in, out, to_coeff=True):
+        f = self._p("pfhe_multi_ggsw#_external_product_slices")
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(self._arr, len(self.tables), k, log_basis, levels or 0, _host_ptr(key, self.bits), _host_ptr(glwe_in, self.bits),
+                _host_ptr(out, self.bits, _size(glwe_in)), _size(glwe_in) // ((k + 1) * self.n), int(bool(to_coeff))))
+        return out
+
+    def bootstrapping_keys(self, log_basis, levels, n_lwe, bsk):
+        """Replicate one bootstrapping key on every device."""
+        return [BootstrappingKey(t, log_basis, levels, n_lwe, bsk) for t in self.tables]
+
+    def bootstrap_slices(self, keys, lwe, test_vector, out=None, extract=True):
+        n_lwe = keys[0].n_lwe
+        batch = _size(lwe) // (n_lwe + 1)
+        width = (self.n + 1) if extract else 2 * self.n
+        if out is None:
+            out = np.empty((batch, width), dtype=_np_dtype(self.bits))
+        karr = (C.c_void_p * len(keys))(*[k._h for k in keys])
+        f = self._p("pfhe_multi_bootstrap#_slices")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(self._arr, karr, len(self.tables), _host_ptr(lwe, 32, batch * (n_lwe + 1)), _host_ptr(test_vector, self.bits, self.n),
+                _host_ptr(out, self.bits, batch * width), batch, int(bool(extract))))
+        return out
+
+
+# ---- whole-ciphertext transforms (primus_lattice/src/macros/mod.rs:537-674) and the byte layout (:39-97) ----
+_SHAPES = {"rlwe": 0, "rlev": 1, "rgsw": 1, "glwe": 1, "glev": 2, "ggsw": 2}
+
+
+def cipher_words(table: _NttTable, shape: str, *dims) -> int:
+    """Word count of a flat ciphertext container: rlwe() / rlev(levels) / rgsw(levels) / glwe(k) / glev(k, levels) / ggsw(k, levels)."""
+    f = getattr(lib(), f"pfhe_{shape}{table.bits}_words"); f.argtypes = [C.c_void_p] + [C.c_uint32] * _SHAPES[shape]; f.restype = C.c_size_t
+    return int(f(table._h, *[int(d) for d in dims]))
+
+
+def into_ntt_form(table: _NttTable, shape: str, data, *dims):
+    """`cipher.into_ntt_form(table)` for the named container: in place on host storage, returns it."""
+    f = getattr(lib(), f"pfhe_{shape}{table.bits}_into_ntt_form"); f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_uint32] * _SHAPES[shape]
+    check(f(table._h, _host_ptr(data, table.bits, cipher_words(table, shape, *dims)), *[int(d) for d in dims]))
+    return data
+
+
+def into_coeff_form(table: _NttTable, shape: str, data, *dims):
+    f = getattr(lib(), f"pfhe_{shape}{table.bits}_into_coeff_form"); f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_uint32] * _SHAPES[shape]
+    check(f(table._h, _host_ptr(data, table.bits, cipher_words(table, shape, *dims)), *[int(d) for d in dims]))
+    return data
+
+
+def write_ntt_form(table: _NttTable, src, dst):
+    f = getattr(lib(), f"pfhe_cipher{table.bits}_write_ntt_form"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    check(f(table._h, _host_ptr(src, table.bits), _host_ptr(dst, table.bits, _size(src)), _size(src)))
+    return dst
+
+
+def write_coeff_form(table: _NttTable, src, dst):
+    f = getattr(lib(), f"pfhe_cipher{table.bits}_write_coeff_form"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    check(f(table._h, _host_ptr(src, table.bits), _host_ptr(dst, table.bits, _size(src)), _size(src)))
+    return dst
+
+
+def dcrt_into_ntt_form(table: _DcrtTable, data):
+    f = getattr(lib(), f"pfhe_dcrt_cipher{table.bits}_into_ntt_form"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    check(f(table._h, _host_ptr(data, table.bits), _size(data)))
+    return data
+
+
+def dcrt_into_coeff_form(table: _DcrtTable, data):
+    f = getattr(lib(), f"pfhe_dcrt_cipher{table.bits}_into_coeff_form"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    check(f(table._h, _host_ptr(data, table.bits), _size(data)))
+    return data
+
+
+def to_bytes(words, bits=64) -> bytes:
+    """`cipher.to_bytes()`: raw little-endian bytes of the flat word array (macros/mod.rs:74-80)."""
+    n = _size(words)
+    out = (C.c_uint8 * (n * bits // 8))()
+    f = getattr(lib(), f"pfhe_cipher{bits}_write_bytes"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    check(f(_host_ptr(words, bits), n, out, len(out)))
+    return bytes(out)
+
+
+def from_bytes(data: bytes, bits=64):
+    """`Cipher::from_bytes(data)`: the flat word array of a serialised container (macros/mod.rs:47-52)."""
+    if len(data) % (bits // 8):
+        raise PfheError(9, "byte length is not a multiple of the word size")
+    out = np.empty(len(data) // (bits // 8), dtype=_np_dtype(bits))
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    f = getattr(lib(), f"pfhe_cipher{bits}_read_bytes"); f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    check(f(_host_ptr(out, bits), out.size, buf, len(data)))
+    return out
+
+
+class UintNttTable:
+    """UintNttTable<T> (primus_ntt/src/ntt/primitive.rs:37-396), T = u16 / u32 / u64: the generic table with its own constructor
+    rules; transforms run the plain radix-2 kernel."""
+
+    def __init__(self, log_n: int, modulus: int, bits: int = 64, device: int = 0):
+        if bits not in (16, 32, 64):
+            raise ValueError("word size must be 16, 32 or 64")
+        self.bits, self.q, self.log_n, self.n = bits, int(modulus), int(log_n), 1 << int(log_n)
+        self._h = C.c_void_p()
+        ct = {16: C.c_uint16, 32: C.c_uint32, 64: C.c_uint64}[bits]
+        if self.q >> bits:
+            raise PfheError(5, "modulus does not fit the word type")
+        f = getattr(lib(), f"pfhe_uintntt{bits}_create"); f.argtypes = [C.c_int, C.c_uint32, ct, C.c_void_p]
+        check(f(device, log_n, self.q, C.byref(self._h)))
+        self._ct = ct
+
+    new = classmethod(lambda cls, log_n, modulus, bits=64, device=0: cls(log_n, modulus, bits, device))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                f = getattr(lib(), f"pfhe_uintntt{self.bits}_destroy"); f.argtypes = [C.c_void_p]; f.restype = None
+                f(self._h); self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def poly_length(self): return self.n
+    def modulus(self): return self.q
+
+    def root(self):
+        f = getattr(lib(), f"pfhe_uintntt{self.bits}_root"); f.argtypes = [C.c_void_p]; f.restype = self._ct
+        return int(f(self._h))
+
+    def inv_root(self):
+        f = getattr(lib(), f"pfhe_uintntt{self.bits}_inv_root"); f.argtypes = [C.c_void_p]; f.restype = self._ct
+        return int(f(self._h))
+
+    def _run(self, name, polys, lazy):
+        if not isinstance(polys, np.ndarray) or polys.dtype.itemsize * 8 != self.bits or not polys.flags.c_contiguous or polys.size % self.n:
+            raise TypeError("expected a C-contiguous numpy array of whole polynomials in the table's word type")
+        f = getattr(lib(), f"pfhe_uintntt{self.bits}_{name}"); f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        check(f(self._h, polys.ctypes.data_as(C.c_void_p), polys.size // self.n, int(lazy)))
+
+    def transform_slice(self, poly): self._run("transform_slices", poly, 0)
+    def lazy_transform_slice(self, poly): self._run("transform_slices", poly, 1)
+    def inverse_transform_slice(self, values): self._run("inverse_transform_slices", values, 0)
+    def lazy_inverse_transform_slice(self, values): self._run("inverse_transform_slices", values, 1)
+    transform_slices = transform_slice
+    inverse_transform_slices = inverse_transform_slice

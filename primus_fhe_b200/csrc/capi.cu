@@ -53,7 +53,7 @@ static void fill_pass_tables(const host::HostTables<T> &h, int loge, std::vector
     }
 }
 
-template <typename T, typename H> static pfhe_status create_handle(int device, uint32_t log_n, T q, H **out) {
+template <typename T, typename H> pfhe_status create_handle(int device, uint32_t log_n, T q, H **out, bool generic_only) {
     using Pair = typename Word<T>::Pair;
     constexpr int BITS = sizeof(T) * 8;
     if (!out) return PFHE_ERR_INVALID_ARG;
@@ -90,7 +90,8 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
         hd->head.fwd_head[k] = fwd[k];
         hd->head.inv_tail[k] = inv[n - 8 + k];
     }
-    const int loge = choose_loge(BITS, (int)log_n), loge_lat = lattice_loge(BITS, (int)log_n);
+    // generic_only: UintNttTable handles always run the generic radix-2 kernel (no register-pass / FP64 layouts)
+    const int loge = generic_only ? 0 : choose_loge(BITS, (int)log_n), loge_lat = generic_only ? 0 : lattice_loge(BITS, (int)log_n);
     if (loge) fill_pass_tables<T>(h, loge, fp, ip);
     if (loge_lat) fill_pass_tables<T>(h, loge_lat, fpl, ipl);
     // FP64-pipe path: u64 words and q < 2^50 (every table value is then an exact double)
@@ -175,14 +176,14 @@ template <typename T, typename H> static pfhe_status create_handle(int device, u
     return PFHE_OK;
 }
 
-template <typename H> static void destroy_handle(H *h) {
+template <typename H> void destroy_handle(H *h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     if (h->blob) cudaFree(h->blob);
     delete h;
 }
 
-template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd, bool lazy = false) {
+template <typename T> pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd, bool lazy) {
     if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
     const size_t bytes = sizeof(T) << t->h.log_n;
     const void *ins[1] = {polys};
@@ -201,7 +202,7 @@ template <typename T> static pfhe_status host_transform(const NttHandle<T> *t, T
     });
 }
 
-template <typename T> static pfhe_status host_polymul(const NttHandle<T> *t, const T *a, const T *b, T *c, size_t batch) {
+template <typename T> pfhe_status host_polymul(const NttHandle<T> *t, const T *a, const T *b, T *c, size_t batch) {
     if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;
     const size_t bytes = sizeof(T) << t->h.log_n;
     const void *ins[2] = {a, b};
@@ -299,7 +300,7 @@ static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size
     pfhe_status s = PFHE_OK;
     for (size_t i = 0; i < count && s == PFHE_OK; i++) {
         H *h = nullptr;
-        s = create_handle<T, H>(device, log_n, moduli[i], &h);
+        s = create_handle<T, H>(device, log_n, moduli[i], &h, false);
         if (s == PFHE_OK) d->limbs.push_back(h);
     }
     if (s == PFHE_OK) {
@@ -342,7 +343,7 @@ static pfhe_status create_dcrt(int device, uint32_t log_n, const T *moduli, size
     return PFHE_OK;
 }
 
-template <typename T, typename D> static pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd, bool lazy) {
+template <typename T, typename D> pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd, bool lazy) {
     if (!t || (!polys && batch)) return PFHE_ERR_INVALID_ARG;
     const size_t L = t->limbs.size();
     const size_t bytes = (sizeof(T) << t->limbs[0]->h.log_n) * L;
@@ -404,7 +405,7 @@ static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t
 // Host-slice shim of the single-modulus external product: key uploaded once, ciphertexts streamed through the pipelined
 // H2D -> kernel -> D2H path (the reference's CrtGlwe::mul_dcrt_ggsw_to works on host slices, primus_data/src/traits.rs:20).
 template <typename T, typename H>
-static pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,
+pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,
                                  int to_coeff) {
     if (!t || ((!key || !in || !out) && batch)) return PFHE_ERR_INVALID_ARG;
     GadgetParams<T> g;
@@ -527,6 +528,19 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
     return PFHE_OK;
 }
 
+template pfhe_status create_handle<uint32_t, pfhe_ntt32>(int, uint32_t, uint32_t, pfhe_ntt32 **, bool);
+template pfhe_status create_handle<uint64_t, pfhe_ntt64>(int, uint32_t, uint64_t, pfhe_ntt64 **, bool);
+template void destroy_handle<pfhe_ntt32>(pfhe_ntt32 *);
+template void destroy_handle<pfhe_ntt64>(pfhe_ntt64 *);
+template pfhe_status host_transform<uint32_t>(const NttHandle<uint32_t> *, uint32_t *, size_t, bool, bool);
+template pfhe_status host_transform<uint64_t>(const NttHandle<uint64_t> *, uint64_t *, size_t, bool, bool);
+template pfhe_status host_polymul<uint32_t>(const NttHandle<uint32_t> *, const uint32_t *, const uint32_t *, uint32_t *, size_t);
+template pfhe_status host_polymul<uint64_t>(const NttHandle<uint64_t> *, const uint64_t *, const uint64_t *, uint64_t *, size_t);
+template pfhe_status ext_prod_host<uint32_t, pfhe_ntt32>(const pfhe_ntt32 *, uint32_t, uint32_t, uint32_t, const uint32_t *, const uint32_t *, uint32_t *, size_t, int);
+template pfhe_status ext_prod_host<uint64_t, pfhe_ntt64>(const pfhe_ntt64 *, uint32_t, uint32_t, uint32_t, const uint64_t *, const uint64_t *, uint64_t *, size_t, int);
+template pfhe_status dcrt_host_transform<uint32_t, pfhe_dcrt32>(const pfhe_dcrt32 *, uint32_t *, size_t, bool, bool);
+template pfhe_status dcrt_host_transform<uint64_t, pfhe_dcrt64>(const pfhe_dcrt64 *, uint64_t *, size_t, bool, bool);
+
 }  // namespace pfhe
 
 extern "C" {
@@ -554,7 +568,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
 
 #define PFHE_DEFINE_WORD(B, T)                                                                                                        \
     pfhe_status pfhe_ntt##B##_create(int device, uint32_t log_n, T q, pfhe_ntt##B **out) {                                            \
-        return create_handle<T, pfhe_ntt##B>(device, log_n, q, out);                                                                  \
+        return create_handle<T, pfhe_ntt##B>(device, log_n, q, out, false);                                                                  \
     }                                                                                                                                 \
     void pfhe_ntt##B##_destroy(pfhe_ntt##B *t) { destroy_handle(t); }                                                                 \
     size_t pfhe_ntt##B##_poly_length(const pfhe_ntt##B *t) { return t ? t->h.n : 0; }                                                 \

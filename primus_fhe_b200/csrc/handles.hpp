@@ -110,15 +110,15 @@ template <typename T> struct DcrtHandle {
 // launch(dev_in_chunks[], dev_out, n_units, stream).
 template <typename LaunchF>
 inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, const size_t *in_bytes, void *host_out, size_t out_bytes,
-                             size_t units, LaunchF launch, int out_alias = -1) {
+                             size_t units, LaunchF launch, int out_alias = -1, size_t scratch_bytes = 0) {
     if (units == 0) return PFHE_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return PFHE_ERR_CUDA;
     cudaStream_t st[kPipe];
     cudaMemPool_t pool = nullptr;
     PFHE_CUDA(t_streams.get(device, st, &pool));
-    size_t per_unit = out_alias >= 0 ? 0 : out_bytes;  // out_alias: the kernel updates input region #out_alias in place
-    for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];
+    size_t per_unit = (out_alias >= 0 ? 0 : out_bytes) + scratch_bytes;  // out_alias: the kernel updates input region #out_alias in place
+    for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];  // scratch_bytes: device-only work area per unit, handed to launch as din[n_in]
     // chunk so that each stage moves ~64 MiB (measured best on PCIe Gen5; PFHE_PIPE_CHUNK_MB overrides); at least one unit
     size_t chunk_bytes = (size_t)64 << 20;
     if (const char *e = getenv("PFHE_PIPE_CHUNK_MB")) {
@@ -132,7 +132,7 @@ inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
     void *dbuf[kPipe] = {};
     pfhe_status status = PFHE_OK;
     for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit, pool, st[i]);
+        cudaError_t e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit + 6 * 256, pool, st[i]);  // + alignment slack of the regions
         if (e != cudaSuccess) {
             status = cuda_fail(e);
             break;
@@ -151,9 +151,10 @@ inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
                 din[i] = base + off;
                 e = cudaMemcpyAsync(base + off, static_cast<const unsigned char *>(host_in[i]) + done * in_bytes[i], nu * in_bytes[i],
                                     cudaMemcpyHostToDevice, st[b]);
-                off += chunk * in_bytes[i];
+                off += (chunk * in_bytes[i] + 255) & ~(size_t)255;  // every region starts 256-byte aligned
             }
             void *dout = out_alias >= 0 ? const_cast<void *>(din[out_alias]) : static_cast<void *>(base + off);
+            if (scratch_bytes && n_in < 4) din[n_in] = base + off + (out_alias >= 0 ? 0 : ((chunk * out_bytes + 255) & ~(size_t)255));
             if (e == cudaSuccess) e = launch(din, dout, nu, st[b]);
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(static_cast<unsigned char *>(host_out) + done * out_bytes, dout, nu * out_bytes, cudaMemcpyDeviceToHost,
@@ -179,3 +180,14 @@ struct pfhe_ntt32 : pfhe::NttHandle<uint32_t> {};
 struct pfhe_ntt64 : pfhe::NttHandle<uint64_t> {};
 struct pfhe_dcrt32 : pfhe::DcrtHandle<uint32_t> {};
 struct pfhe_dcrt64 : pfhe::DcrtHandle<uint64_t> {};
+
+namespace pfhe {
+// defined in capi.cu (explicitly instantiated for the u32 / u64 handle types)
+template <typename T, typename H> pfhe_status create_handle(int device, uint32_t log_n, T q, H **out, bool generic_only);
+template <typename H> void destroy_handle(H *h);
+template <typename T> pfhe_status host_transform(const NttHandle<T> *t, T *polys, size_t batch, bool fwd, bool lazy);
+template <typename T> pfhe_status host_polymul(const NttHandle<T> *t, const T *a, const T *b, T *c, size_t batch);
+template <typename T, typename H>
+pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch, int to_coeff);
+template <typename T, typename D> pfhe_status dcrt_host_transform(const D *t, T *polys, size_t batch, bool fwd, bool lazy);
+}  // namespace pfhe

@@ -147,11 +147,14 @@ ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<t
     }
 }
 
-template <typename F, int LOGN, int LOGE, int PPB>
-__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, polymul_min_blocks<F, LOGN, LOGE, PPB>())
+// STASH: the register file cannot hold two tiles of 2^LOGE words (u64, E = 32: 128 registers of data alone), so fwd(a) is parked in
+// the OUTPUT polynomial (canonical words, bit-reversed order; it stays in L2: one polynomial per SM is in flight) and read back by
+// the thread that owns the same words after fwd(b).  Without it the N = 8192 / 16384 products spill (r01: 0.12 of the HBM peak on
+// the 8-limb N = 16384 RNS product).  The host swaps a and b when c aliases b, and uses the two-tile kernel when a == b == c.
+template <typename F, int LOGN, int LOGE, int PPB, bool STASH = false>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, STASH ? ntt_min_blocks<F, LOGN, LOGE, PPB>() : polymul_min_blocks<F, LOGN, LOGE, PPB>())
 polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
-               const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, typename F::WordT *__restrict__ cc,
-               size_t npolys) {
+               const typename F::WordT *a, const typename F::WordT *b, typename F::WordT *cc, size_t npolys) {
     using Core = NttCore<F, LOGN, LOGE>;
     using T = typename F::WordT;
     using Elem = typename F::Elem;
@@ -168,15 +171,42 @@ polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
     const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);
     const typename F::Ctx c = F::ctx(tb);
     typename SyncFor<TPP>::type sync;
-    Elem xa[E], xb[E];
-    Core::forward_g2r(a + poly * N, xa, sm, tb, c, t, sync);
-    sync();  // the exchange buffer is reused with the first pass's pattern
-    Core::forward_g2r(b + poly * N, xb, sm, tb, c, t, sync);
-    // pointwise product, exact mod q (BarrettModulus::reduce_mul, primus_modulus/src/barrett/ops.rs:276-283)
+    if constexpr (STASH) {
+        static_assert(PPB == 1, "the stash variant runs one polynomial per CTA");
+        T *g_c = cc + poly * N;
+        Elem x[E];
+        Core::forward_g2r(a + poly * N, x, sm, tb, c, t, sync);
+        Core::fwd_regs_to_sm(x, sm, c, t);
+        sync();
+        Core::copy_s2g(sm, g_c, t);      // fwd(a), canonical, parked in the output polynomial
+        sync();                          // buffer free again; the CTA's global writes are visible to the CTA after the barrier
+        Core::forward_g2r(b + poly * N, x, sm, tb, c, t, sync);
+        // this thread's words of fwd(a): the same contiguous run [t*E, (t+1)*E) it now holds of fwd(b) (coherent loads: written above)
+        const T *ga = g_c + (size_t)t * E;
+        constexpr int CW = Core::CW;  // 16-byte vectors, a few in flight at a time (the register file is full)
 #pragma unroll
-    for (int j = 0; j < E; j++) xa[j] = F::pointwise(xa[j], xb[j], c);
-    Core::template inv_from<Core::P::NPASS - 1>(xa, sm, tb, c, t, sync);
-    if (active) Core::inv_regs_to_global(xa, cc + poly * N, c, t);
+        for (int v = 0; v < E / CW; v++) {
+            typename Core::WVec w;
+            uint4 raw;
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(ga + v * CW) : "memory");
+            *reinterpret_cast<uint4 *>(&w) = raw;
+#pragma unroll
+            for (int k = 0; k < CW; k++) x[v * CW + k] = F::pointwise(F::load(w.v[k], c), x[v * CW + k], c);
+        }
+        sync();                          // every thread has read its stash before the output polynomial is overwritten
+        Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, c, t, sync);
+        Core::inv_regs_to_global(x, g_c, c, t);
+    } else {
+        Elem xa[E], xb[E];
+        Core::forward_g2r(a + poly * N, xa, sm, tb, c, t, sync);
+        sync();  // the exchange buffer is reused with the first pass's pattern
+        Core::forward_g2r(b + poly * N, xb, sm, tb, c, t, sync);
+        // pointwise product, exact mod q (BarrettModulus::reduce_mul, primus_modulus/src/barrett/ops.rs:276-283)
+#pragma unroll
+        for (int j = 0; j < E; j++) xa[j] = F::pointwise(xa[j], xb[j], c);
+        Core::template inv_from<Core::P::NPASS - 1>(xa, sm, tb, c, t, sync);
+        if (active) Core::inv_regs_to_global(xa, cc + poly * N, c, t);
+    }
 }
 
 
@@ -504,6 +534,21 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
             };
             if (limbs > 1) return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, true>);
             return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, false>);
+        }
+    }
+    if constexpr (sizeof(T) == 8 && LOGE == 5 && LOGN >= 13 && PPB == 1) {
+        static const bool use_stash = env_int("PFHE_POLYMUL_STASH", 1) != 0;  // A/B tuning hook
+        if (c == b) {  // the stash would overwrite b before it is read: the product commutes
+            const T *tmp = a;
+            a = b;
+            b = tmp;
+        }
+        if (use_stash && c != b) {
+            auto ks = polymul_kernel<F, LOGN, LOGE, PPB, true>;
+            if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            ks<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
+            count_launch();
+            return cudaGetLastError();
         }
     }
     auto k = polymul_kernel<F, LOGN, LOGE, PPB>;

@@ -363,6 +363,22 @@ template <typename T> __global__ void __launch_bounds__(256) modmul_bench_kernel
     if (acc == (T)0x1234567) sink[0] = acc;
 }
 
+// 8 independent chains of bare Shoup products per thread (1 high + 2 low multiplies, nothing else): the "modmul ops at
+// integer-pipe peak" denominator of the lattice-kernel rooflines.
+template <typename T> __global__ void __launch_bounds__(256) shoup_bench_kernel(T q, T w, T wq, uint32_t iters, T *sink) {
+    T x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = (T)(threadIdx.x * 7 + k + blockIdx.x) % q;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = shoup_lazy<T>(x[k], w, wq, q);
+    }
+    T acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc ^= x[k];
+    if (acc == (T)0x1234567) sink[0] = acc;
+}
+
 cudaError_t run_modmul_microbench(int kind, uint32_t blocks, uint32_t iters, float *ms) {
     cudaEvent_t e0, e1;
     cudaError_t e;
@@ -375,6 +391,12 @@ cudaError_t run_modmul_microbench(int kind, uint32_t blocks, uint32_t iters, flo
         if (kind == 0) {
             const uint32_t q = 132120577u, w = 73993u;
             modmul_bench_kernel<uint32_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint32_t>(w, q), iters, (uint32_t *)sink);
+        } else if (kind == 2) {
+            const uint32_t q = 132120577u, w = 73993u;
+            shoup_bench_kernel<uint32_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint32_t>(w, q), iters, (uint32_t *)sink);
+        } else if (kind == 3) {
+            const uint64_t q = 1152921504606830593ull, w = 459811883340678ull;
+            shoup_bench_kernel<uint64_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint64_t>(w, q), iters, (uint64_t *)sink);
         } else {
             const uint64_t q = 1125899906826241ull, w = 46909545429ull;
             modmul_bench_kernel<uint64_t><<<blocks, 256>>>(q, w, host::shoup_quot<uint64_t>(w, q), iters, (uint64_t *)sink);

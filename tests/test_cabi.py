@@ -100,3 +100,37 @@ def test_host_only_handles_match_oracle_without_gpu():
     with pytest.raises(P.PfheError) as e:
         P.BaseConverter([], [29])
     assert e.value.name == "EmptyBase"
+
+
+def test_round2_host_only_entry_points_without_gpu():
+    """Byte layout (macros/mod.rs:39-97) and the UintNttTable constructor rules (primitive.rs:114-181) are host-side: they work and
+    fail exactly the same on a CPU-only host."""
+    import numpy as np
+    import pytest
+    import primus_fhe_b200 as P
+    rng = np.random.default_rng(7)
+    for bits, dt in ((32, np.uint32), (64, np.uint64)):
+        w = rng.integers(0, 1 << 27, 257, dtype=np.uint64).astype(dt)
+        b = P.to_bytes(w, bits)
+        assert b == w.astype(w.dtype.newbyteorder("<")).tobytes() and len(b) == w.size * bits // 8
+        assert np.array_equal(P.from_bytes(b, bits), w)
+        assert np.array_equal(P.from_bytes(b"\x01" + b[1:], bits)[1:], w[1:])
+        with pytest.raises(P.PfheError):
+            P.from_bytes(b[:-1], bits)
+    for bits, q, log_n, name in ((16, 12289, 13, "NoPrimitiveRoot"), (32, 132120577, 21, "NoPrimitiveRoot"), (16, 40961, 10, "ModulusTooLarge"),
+                                 (32, 3221225473, 10, "ModulusTooLarge"), (64, 97, 7, "NoPrimitiveRoot"), (64, 1152921504606830593 * 4 + 1, 3, None)):
+        with pytest.raises(P.PfheError) as e:
+            P.UintNttTable(log_n, q, bits)
+        assert name is None or e.value.name == name
+
+
+def test_shard_rule_matches_the_c_abi_documentation():
+    """pfhe_multi_* documents shard r of `total` over n parts as starting at r*floor(total/n) + min(r, total mod n): the same rule
+    as primus_fhe_b200.shard.shard_range (checked here so the two cannot drift)."""
+    from primus_fhe_b200.shard import shard_range
+    for total in (0, 1, 7, 1250, 10000, 65537):
+        for n in (1, 2, 3, 8):
+            for r in range(n):
+                b = r * (total // n) + min(r, total % n)
+                e = b + total // n + (1 if r < total % n else 0)
+                assert shard_range(total, n, r) == (b, e)

@@ -23,3 +23,8 @@ for nrns in (256, 1024):
     ms = timeit(lambda: dc.forward_batch(ra)); print(f"DCRT fwd: {8*nrns/ms*1e3:.3e} limb NTT/s")
     ms = timeit(lambda: t1.forward_batch(a1)); print(f"single fwd: {8*nrns/ms*1e3:.3e} NTT/s")
     del ra, rb, rc
+
+t13 = P.U64NttTable(13, 1125899906826241)
+x = torch.randint(0, 1125899906826241, (16384, 8192), dtype=torch.int64, device="cuda"); y = x.flip(0).contiguous(); z = torch.empty_like(x)
+ms = timeit(lambda: t13.polymul_batch(x, y, z)); print(f"polymul N=8192 u64 q50 batch 16384: {16384/ms*1e3:.3e} /s")
+ms = timeit(lambda: t13.forward_batch(x)); print(f"fwd N=8192: {16384/ms*1e3:.3e} /s")

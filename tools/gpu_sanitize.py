@@ -36,5 +36,22 @@ key = dev(np.stack([rng.integers(0, m, (2 * 4 * 2, 1024), dtype=np.uint64) for m
 cin = dev(np.stack([rng.integers(0, m, (2 * 2, 1024), dtype=np.uint64) for m in mods], axis=1), 64).contiguous()
 out = torch.empty_like(cin)
 P.dcrt_external_product_batch(dc2, bb, 1, key, cin, out, True)
+# round 2: N = 16384 fused product (stash variant), bootstrap shim (lattice32.cu + extract), multi-device driver, modulus switch, UintNttTable
+t14 = P.U64NttTable(14, 1125899904679937)
+x = dev(rng.integers(0, 1125899904679937, (2, 16384), dtype=np.uint64), 64); y = torch.empty_like(x)
+t14.polymul_batch(x, x.flip(0).contiguous(), y)
+t10 = P.U32NttTable(10, 132120577)
+lv = P.ApproxSignedBasis(132120577, 7, None, 32).decompose_length()
+bskh = rng.integers(0, 132120577, 3 * 2 * lv * 2 * 1024, dtype=np.uint64).astype(np.uint32)
+lweh = rng.integers(0, 2048, (3, 4), dtype=np.uint64).astype(np.uint32)
+tvh = rng.integers(0, 132120577, 1024, dtype=np.uint64).astype(np.uint32)
+key = P.BootstrappingKey(t10, 7, None, 3, bskh)
+key.bootstrap_slices(lweh, tvh)
+mt = P.MultiNttTable(10, 132120577, [0, 0], 32)
+mt.bootstrap_slices(mt.bootstrapping_keys(7, None, 3, bskh), lweh, tvh)
+h = rng.integers(0, 132120577, (5, 1024), dtype=np.uint64).astype(np.uint32); mt.transform_slices(h)
+v = dev(rng.integers(0, 132120577, 4096, dtype=np.uint64), 32); o = torch.empty(4096, dtype=torch.int32, device="cuda")
+P.modulus_switch_batch(132120577, 11, v, o, 32)
+u = P.UintNttTable(10, 12289, 16); a = rng.integers(0, 12289, (2, 1024), dtype=np.uint64).astype(np.uint16); u.transform_slices(a); u.inverse_transform_slices(a)
 torch.cuda.synchronize()
 print("sanitize workload ok")
