@@ -439,6 +439,16 @@ pfhe_status pfhe_bootstrap64_slices(const pfhe_ntt64 *t, const pfhe_bsk64 *bsk, 
                                     uint64_t *out, size_t batch, int extract);
 pfhe_status pfhe_bootstrap32_slices(const pfhe_ntt32 *t, const pfhe_bsk32 *bsk, const uint32_t *lwe, const uint32_t *test_vector,
                                     uint32_t *out, size_t batch, int extract);
+/* Ternary-secret blind rotation by monomial combination (composed from the reference's primitives, parity unpinned
+ * like the binary form): for every LWE coefficient a_i the accumulator is multiplied by RGSW(X^(a_i s_i)), s_i in {-1,0,1}, with ONE
+ * external product against  K_i = (NTT(X^a_i) - 1) .* BSK+_i + (NTT(X^-a_i) - 1) .* BSK-_i, where NTT(X^d) is
+ * NttTable::transform_coeff_one_monomial(d) (primus_ntt/src/ntt/prime64/table.rs:611-651) and BSK+-_i = RGSW([s_i = +-1]) in NTT form:
+ *     ACC <- ACC + INTT( sum_{r,l} NTT(digit_l(ACC_r)) .* K_i[r][l][c] ).
+ * bsk_plus / bsk_minus: device [n_lwe][2][levels][2][N]; other arguments as pfhe_blind_rotate32_batch.
+ * Implemented for the bootstrapping shape of BASELINE config 5 (u32 words, N = 1024); PFHE_ERR_UNSUPPORTED otherwise. */
+pfhe_status pfhe_blind_rotate_ternary32_batch(const pfhe_ntt32 *t, uint32_t log_basis, uint32_t levels_in, const uint32_t *bsk_plus,
+                                              const uint32_t *bsk_minus, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
+                                              uint32_t *acc_out, size_t batch, void *stream);
 /* LWE modulus switch to Z_2N before blind rotation (NOT in the reference -- it has no bootstrapping; convention fixed here and
  * in the oracle): out[i] = floor((lwe[i] * 2N + floor(q/2)) / q) mod 2N, exact integer arithmetic; 2N = 2^log_2n.
  * lwe: device, `count` canonical words (all a_i and b of a batch); out: device uint32. */

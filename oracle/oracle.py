@@ -648,3 +648,30 @@ def modulus_switch(lwe, q, log_2n):
     two_n = 1 << log_2n
     flat = [((int(v) * two_n + q // 2) // q) % two_n for v in np.asarray(lwe).reshape(-1)]
     return np.array(flat, dtype=np.uint32).reshape(np.asarray(lwe).shape)
+
+
+def blind_rotate_ternary(table: _NttTable, basis: ApproxSignedBasis, bsk_plus, bsk_minus, n_lwe, lwe, test_vector, batch=1):
+    """Ternary-secret blind rotation by monomial combination (NOT in the reference -- composed from its primitives):
+    ACC <- (0, tv * X^(2N-b)); for every i: K = (NTT(X^a_i) - 1) .* BSK+_i + (NTT(X^-a_i) - 1) .* BSK-_i (transform_coeff_one_monomial,
+    prime64/table.rs:611-651; slice ops), ACC <- ACC + into_coeff_form(mul_dcrt_ggsw_to(ACC, K)) (glwe/crt.rs:200-227)."""
+    bits, n, q = table.bits, table.n, table.q
+    dt = _np(bits)
+    bsk_plus, bsk_minus, tv = _arr(bsk_plus, bits), _arr(bsk_minus, bits), _arr(test_vector, bits)
+    lwe = np.ascontiguousarray(lwe, dtype=np.uint32).reshape(batch, n_lwe + 1)
+    levels = basis.decompose_length()
+    rgsw = 2 * levels * 2 * n
+    out = np.empty((batch, 2 * n), dtype=dt)
+    for b in range(batch):
+        acc = np.zeros(2 * n, dtype=dt)
+        acc[n:] = mul_monomial(tv, (2 * n - int(lwe[b, n_lwe])) % (2 * n), q, bits)
+        for i in range(n_lwe):
+            a = int(lwe[b, i]) % (2 * n)
+            mp = (table.transform_coeff_one_monomial(a).astype(object) - 1) % q
+            mm = (table.transform_coeff_one_monomial((2 * n - a) % (2 * n)).astype(object) - 1) % q
+            kp = bsk_plus[i * rgsw:(i + 1) * rgsw].astype(object).reshape(-1, n)
+            km = bsk_minus[i * rgsw:(i + 1) * rgsw].astype(object).reshape(-1, n)
+            key = ((kp * mp + km * mm) % q).astype(dt).reshape(-1)
+            prod = external_product_single(table, basis, 1, key, acc.reshape(1, -1), to_coeff=True, batch=1, threads=1)[0]
+            acc = ((acc.astype(object) + prod.astype(object)) % q).astype(dt)
+        out[b] = acc
+    return out

@@ -225,6 +225,17 @@ class _NttTable:
                 _dev_ptr(test_vector, self.bits, self.n), _dev_ptr(acc_out, self.bits, batch * 2 * self.n), batch, _stream()))
 
 
+    def blind_rotate_ternary_batch(self, log_basis, levels, bsk_plus, bsk_minus, n_lwe, lwe, test_vector, acc_out):
+        """Ternary-secret blind rotation by monomial combination (pfhe_blind_rotate_ternary32_batch; u32, N = 1024)."""
+        if self.bits != 32:
+            raise PfheError(10, "ternary blind rotation is built for u32 words")
+        f = lib().pfhe_blind_rotate_ternary32_batch
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        batch = lwe.numel() // (n_lwe + 1)
+        check(f(self._h, log_basis, levels or 0, _dev_ptr(bsk_plus, 32), _dev_ptr(bsk_minus, 32, bsk_plus.numel()), n_lwe, _dev_ptr(lwe, 32),
+                _dev_ptr(test_vector, 32, self.n), _dev_ptr(acc_out, 32, batch * 2 * self.n), batch, _stream()))
+
+
 class U64NttTable(_NttTable):
     bits = 64
 

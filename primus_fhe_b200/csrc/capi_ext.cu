@@ -398,6 +398,19 @@ extern "C" {
 PFHE_DEFINE_EXT(32, uint32_t)
 PFHE_DEFINE_EXT(64, uint64_t)
 
+pfhe_status pfhe_blind_rotate_ternary32_batch(const pfhe_ntt32 *t, uint32_t log_basis, uint32_t levels_in, const uint32_t *bsk_plus,
+                                              const uint32_t *bsk_minus, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
+                                              uint32_t *acc_out, size_t batch, void *stream) {
+    if (!t || ((!bsk_plus || !bsk_minus || !lwe || !test_vector || !acc_out) && batch)) return PFHE_ERR_INVALID_ARG;
+    GadgetParams<uint32_t> g;
+    if (!make_gadget<uint32_t>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
+    PFHE_CUDA(launch_blind_rotate_ternary32(t->dev_lat, t->head, g, bsk_plus, bsk_minus, n_lwe, lwe, test_vector, acc_out, batch,
+                                            static_cast<cudaStream_t>(stream)));
+    return PFHE_OK;
+}
+
 /* ---- UintNttTable<T> ---- */
 #define PFHE_DEFINE_UINT(B, T)                                                                                                   \
     pfhe_status pfhe_uintntt##B##_create(int device, uint32_t log_n, T q, pfhe_uintntt##B **out) {                               \

@@ -73,6 +73,10 @@ template <typename T> struct LatHead {
 cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
                                        const uint32_t *bsk, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
                                        uint32_t *acc_out, size_t batch, cudaStream_t stream);
+// ternary-secret (monomial-combination) blind rotation, same shape restrictions
+cudaError_t launch_blind_rotate_ternary32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
+                                          const uint32_t *bsk_plus, const uint32_t *bsk_minus, uint32_t n_lwe, const uint32_t *lwe,
+                                          const uint32_t *test_vector, uint32_t *acc_out, size_t batch, cudaStream_t stream);
 template <typename T>
 cudaError_t launch_external_product(const DevNtt<T> &tb, const GadgetParams<T> &g, uint32_t k, const T *key, const T *in,
                                     T *out, size_t batch, bool to_coeff, cudaStream_t stream);

@@ -55,6 +55,8 @@ struct Params {
     uint2 fwd_head[8];       // fwd[0..7]: twiddles of stages 0..2 (uniform over the polynomial)
     uint2 inv_tail[8];       // inv[N-8 .. N-1]: twiddles of the last three inverse stages (entry 7 unused here)
     const uint2 *fwd, *inv;  // tables in the reference's index order, (w, floor(w 2^32 / q)) pairs
+    const uint32_t *ordinal; // psi^k, k < 2N (monomial transforms, prime32/table.rs; ternary rotation only)
+    uint32_t r32, r32_q;     // 2^32 mod q and its Shoup quotient (Montgomery form of the monomial factors)
 };
 
 __device__ __forceinline__ uint32_t shoup_lazy32(uint32_t y, uint2 w, uint32_t q) { return y * w.x - __umulhi(y, w.y) * q; }
@@ -379,6 +381,116 @@ blind_rotate_n1024_kernel(const __grid_constant__ Params P, const uint32_t *__re
     for (int i = t; i < 2 * N; i += TPP) o[i] = accs[i];
 }
 
+// Ternary-secret ("monomial combination") blind rotation, SURVEY.md 8(f)2.  Per LWE coefficient a_i the accumulator is multiplied by
+// RGSW(X^(a_i s_i)), s_i in {-1, 0, 1}, through ONE external product with the combined key
+//     K_i = (NTT(X^a_i) - 1) .* BSK+_i + (NTT(X^-a_i) - 1) .* BSK-_i
+// (NTT(X^d) = NttTable::transform_coeff_one_monomial(d), primus_ntt/src/ntt/prime64/table.rs:611-651; NTT(1) = all ones):
+//     ACC <- ACC + INTT( sum_{r,l} fwd(digit_l(ACC_r)) .* K_i[r][l][c] ).
+// K_i is never formed: the monomial factors are constant over (r, l), so the lazy sums against BSK+ and BSK- are kept apart and
+// combined once per output coefficient:  sum fwd(d) .* K = m+ .* (sum fwd(d) .* BSK+) + m- .* (sum fwd(d) .* BSK-)  (exact mod q).
+template <int MINB>
+__global__ void __launch_bounds__(TPP, MINB)
+blind_rotate_ternary_n1024_kernel(const __grid_constant__ Params P, const uint32_t *__restrict__ bsk_plus, const uint32_t *__restrict__ bsk_minus,
+                                  uint32_t n_lwe, const uint32_t *__restrict__ lwe, const uint32_t *__restrict__ test_vector,
+                                  uint32_t *__restrict__ acc_out) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *e1 = smem, *e2 = smem + 4 * E1W, *accs = smem + 4 * E1W + 2 * E2W;
+    const int t = threadIdx.x;
+    const size_t ct = blockIdx.x;
+    const uint32_t q = P.q, two_q = P.two_q;
+    const uint32_t *my_lwe = lwe + ct * (size_t)(n_lwe + 1);
+    constexpr uint32_t kMask2N = 2 * N - 1;
+    {
+        const uint32_t b = __ldg(my_lwe + n_lwe) & kMask2N;
+        const uint32_t rot = (2 * N - b) & kMask2N;
+        for (int i = t; i < N; i += TPP) {
+            accs[i] = 0;
+            const uint32_t srcw = ((uint32_t)i - rot) & kMask2N;
+            const uint32_t v = __ldg(test_vector + (srcw & (N - 1)));
+            accs[N + i] = (srcw >= (uint32_t)N) ? (v == 0 ? 0u : q - v) : v;
+        }
+    }
+    __syncthreads();
+    const uint32_t levels = P.levels;
+    const size_t rgsw_len = (size_t)2 * levels * 2 * N;
+    // exponent base of this thread's NTT-domain words i = 8t + m: (2 brv(i) + 1)
+    uint32_t odd[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) odd[m] = 2u * (__brev((uint32_t)(8 * t + m)) >> (32 - LOGN)) + 1u;
+    const uint2 r32 = make_uint2(P.r32, P.r32_q);
+    int par = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_lwe; i++) {
+        const uint32_t a = __ldg(my_lwe + i) & kMask2N;
+        const uint32_t *kp0 = bsk_plus + (size_t)i * rgsw_len + (size_t)t * 8, *km0 = bsk_minus + (size_t)i * rgsw_len + (size_t)t * 8;
+        uint32_t W[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t d = accs[r * N + j * 128 + t];  // canonical
+                W[r][j] = d + (d >= P.threshold ? P.add_r : P.r);
+            }
+        uint64_t accp[2][8], accm[2][8];
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int m = 0; m < 8; m++) accp[c][m] = accm[c][m] = 0;
+#pragma unroll 1
+        for (uint32_t lv = 0; lv < levels; lv++) {
+            const uint32_t shift = P.drop_bits + lv * P.log_basis;
+            uint32_t x[2][8];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) x[r][j] = ((W[r][j] >> shift) & P.mask) + P.digit_off;
+            forward_pair<2>(x, P, e1 + par * 2 * E1W, e2, t, q, two_q);
+            par ^= 1;
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const size_t off = ((size_t)(r * levels + lv) * 2 + c) * N;
+                    const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(kp0 + off)), p1 = __ldg(reinterpret_cast<const uint4 *>(kp0 + off) + 1);
+                    const uint4 m0 = __ldg(reinterpret_cast<const uint4 *>(km0 + off)), m1 = __ldg(reinterpret_cast<const uint4 *>(km0 + off) + 1);
+                    const uint32_t kp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, km[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        accp[c][m] += (uint64_t)x[r][m] * kp[m];
+                        accm[c][m] += (uint64_t)x[r][m] * km[m];
+                    }
+                }
+        }
+        // monomial factors of this step in Montgomery form: (NTT(X^{+-a}) - 1) * 2^32 mod q
+        uint32_t y[2][8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const uint32_t e = (odd[m] * a) & kMask2N;
+            const uint32_t wp = __ldg(P.ordinal + e) - 1u, wm = __ldg(P.ordinal + ((2 * N - e) & kMask2N)) - 1u;   // canonical, >= 0
+            const uint32_t mp = shoup_lazy32(wp, r32, q), mm = shoup_lazy32(wm, r32, q);                           // [0, 2q)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint32_t yp = (uint32_t)(accp[c][m] >> 32) + q - __umulhi((uint32_t)accp[c][m] * P.qinv, q);   // (0, (terms+1) q]
+                const uint32_t ym = (uint32_t)(accm[c][m] >> 32) + q - __umulhi((uint32_t)accm[c][m] * P.qinv, q);
+                const uint64_t s = (uint64_t)yp * mp + (uint64_t)ym * mm;                                           // < 4 (terms+1) q^2 < 2^64
+                y[c][m] = (uint32_t)(s >> 32) + q - __umulhi((uint32_t)s * P.qinv, q);                               // <= first_inv_bias
+            }
+        }
+        inverse_pair<2>(y, P, e1 + par * 2 * E1W, e2, t, q, two_q);
+        par ^= 1;
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t s = accs[c * N + j * 128 + t] + y[c][j];
+                accs[c * N + j * 128 + t] = min(s, s - q);
+            }
+        __syncthreads();
+    }
+    uint32_t *o = acc_out + ct * 2 * N;
+    for (int i = t; i < 2 * N; i += TPP) o[i] = accs[i];
+}
+
 static uint32_t inv_mod_2_32(uint32_t q) {  // q odd
     uint32_t x = q;  // 3 correct bits
     for (int i = 0; i < 5; i++) x *= 2u - q * x;
@@ -387,22 +499,18 @@ static uint32_t inv_mod_2_32(uint32_t q) {  // q odd
 
 }  // namespace br32
 
-// Returns cudaErrorNotSupported when the shape / modulus does not qualify (the caller then uses the generic kernel).
-cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
-                                       const uint32_t *bsk, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *tv, uint32_t *acc_out,
-                                       size_t batch, cudaStream_t stream) {
+static bool build_params(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g, uint64_t terms, br32::Params &P) {
     using namespace br32;
-    static const bool off = getenv("PFHE_BR_FAST") && getenv("PFHE_BR_FAST")[0] == '0';  // A/B tuning hook
-    if (off || tb.log_n != LOGN) return cudaErrorNotSupported;
-    const uint64_t q = tb.q, terms = 2ull * g.levels;
-    if ((2ull * LOGN + 2) * q >= (1ull << 32) || 2 * (terms + 1) * q >= (1ull << 32)) return cudaErrorNotSupported;
-    if (batch == 0) return cudaSuccess;
-    Params P{};
+    if (tb.log_n != LOGN) return false;
+    const uint64_t q = tb.q;
+    if ((2ull * LOGN + 2) * q >= (1ull << 32) || 2 * (terms + 1) * q >= (1ull << 32)) return false;
     P.q = tb.q;
     P.two_q = tb.two_q;
-    P.qinv = inv_mod_2_32(tb.q);
+    P.qinv = br32::inv_mod_2_32(tb.q);
     P.one_q = (uint32_t)((1ull << 32) / q);
     const uint32_t r32 = (uint32_t)((1ull << 32) % q);
+    P.r32 = r32;
+    P.r32_q = host::shoup_quot<uint32_t>(r32, tb.q);
     P.invn_r = host::mulmod<uint32_t>(tb.inv_n, r32, tb.q);
     P.invn_r_q = host::shoup_quot<uint32_t>(P.invn_r, tb.q);
     P.invnw_r = host::mulmod<uint32_t>(head.inv_tail[7].x, r32, tb.q);
@@ -426,6 +534,37 @@ cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead
     }
     P.fwd = tb.fwd;
     P.inv = tb.inv;
+    P.ordinal = tb.ordinal;
+    return true;
+}
+
+// Ternary-secret blind rotation (pfhe_blind_rotate_ternary32_batch); cudaErrorNotSupported outside the u32 / N = 1024 shape.
+cudaError_t launch_blind_rotate_ternary32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
+                                          const uint32_t *bsk_plus, const uint32_t *bsk_minus, uint32_t n_lwe, const uint32_t *lwe,
+                                          const uint32_t *tv, uint32_t *acc_out, size_t batch, cudaStream_t stream) {
+    using namespace br32;
+    Params P{};
+    // every Montgomery output is at most (terms + 1) q with terms = 2 levels; the combined value is below 2q
+    if (!build_params(tb, head, g, 2ull * g.levels, P)) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    constexpr size_t smem = sizeof(uint32_t) * SMEM_WORDS;
+    auto k = blind_rotate_ternary_n1024_kernel<3>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<(unsigned)batch, TPP, smem, stream>>>(P, bsk_plus, bsk_minus, n_lwe, lwe, tv, acc_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when the shape / modulus does not qualify (the caller then uses the generic kernel).
+cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
+                                       const uint32_t *bsk, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *tv, uint32_t *acc_out,
+                                       size_t batch, cudaStream_t stream) {
+    using namespace br32;
+    static const bool off = getenv("PFHE_BR_FAST") && getenv("PFHE_BR_FAST")[0] == '0';  // A/B tuning hook
+    Params P{};
+    if (off || !build_params(tb, head, g, 2ull * g.levels, P)) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
     constexpr size_t smem = sizeof(uint32_t) * SMEM_WORDS;
     const char *e = getenv("PFHE_BR_MINB");  // tuning hook: resident CTAs per SM the register allocator is asked for
     const int mb = e ? atoi(e) : 4;

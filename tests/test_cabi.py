@@ -134,3 +134,20 @@ def test_shard_rule_matches_the_c_abi_documentation():
                 b = r * (total // n) + min(r, total % n)
                 e = b + total // n + (1 if r < total % n else 0)
                 assert shard_range(total, n, r) == (b, e)
+
+
+def test_rust_ffi_crate_bindings_are_complete_and_current():
+    """ffi/primus_cuda/src/sys.rs is generated from include/pfhe.h (tools/gen_rust_sys.py): it must be current and declare every
+    exported symbol, and the safe wrappers must only call symbols that exist."""
+    import os, re, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0, \
+        "run `python tools/gen_rust_sys.py` after editing include/pfhe.h"
+    sys_rs = open(os.path.join(root, "ffi", "primus_cuda", "src", "sys.rs")).read()
+    declared = set(re.findall(r"pub fn (pfhe_[a-z0-9_]+)\(", sys_rs))
+    import primus_fhe_b200 as P
+    assert declared == set(P.declared_symbols())
+    for f in ("ntt.rs", "dcrt.rs", "bootstrap.rs", "multi.rs", "lib.rs"):
+        used = set(re.findall(r"\b(pfhe_[a-z0-9]+_[a-z0-9_]+)\b", open(os.path.join(root, "ffi", "primus_cuda", "src", f)).read()))
+        used = {u for u in used if not re.fullmatch(r"pfhe_(ntt|dcrt|bsk|rns|baseconv|uintntt)(16|32|64)", u)} - {"pfhe_status", "pfhe_cuda", "pfhe_slice_op"}
+        assert used <= declared, (f, used - declared)

@@ -170,3 +170,30 @@ def test_uint_ntt_table_words_and_rules():
         with pytest.raises(P.PfheError) as e:
             P.UintNttTable(log_n, q, bits)
         assert e.value.name == name, (bits, q, log_n, e.value.name)
+
+
+@pytest.mark.parametrize("log_basis,levels,n_lwe,batch", [(7, None, 40, 5), (4, 5, 6, 3), (9, None, 6, 3)])
+def test_ternary_blind_rotation_matches_oracle(log_basis, levels, n_lwe, batch):
+    """pfhe_blind_rotate_ternary32_batch == the oracle's composition (monomial NTTs + slice ops + external product), bit for bit."""
+    import torch
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    q, n = Q27, 1024
+    gt, ot = P.U32NttTable(10, q), O.U32NttTable(10, q)
+    ob = O.ApproxSignedBasis(q, log_basis, levels, 32); lv = ob.decompose_length()
+    rng = np.random.default_rng(206)
+    bp = rng.integers(0, q, n_lwe * 2 * lv * 2 * n, dtype=np.uint64).astype(np.uint32)
+    bm = rng.integers(0, q, n_lwe * 2 * lv * 2 * n, dtype=np.uint64).astype(np.uint32)
+    lwe = rng.integers(0, 2 * n, (batch, n_lwe + 1), dtype=np.uint64).astype(np.uint32)
+    lwe[0, :] = 0
+    lwe[1, :] = 2 * n - 1
+    tv = rng.integers(0, q, n, dtype=np.uint64).astype(np.uint32)
+    want = O.blind_rotate_ternary(ot, ob, bp, bm, n_lwe, lwe, tv, batch=batch)
+    d = lambda x: torch.from_numpy(x.view(np.int32)).cuda()
+    out = torch.empty((batch, 2 * n), dtype=torch.int32, device="cuda")
+    gt.blind_rotate_ternary_batch(log_basis, levels, d(bp), d(bm), n_lwe, d(lwe), d(tv), out)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want)
+    with pytest.raises(P.PfheError):   # other shapes: Unsupported, stated in pfhe.h
+        t11 = P.U32NttTable(11, q)
+        t11.blind_rotate_ternary_batch(log_basis, levels, d(bp), d(bm), 1, d(lwe[:1, :2].copy()), d(np.zeros(2048, np.uint32)),
+                                       torch.empty((1, 4096), dtype=torch.int32, device="cuda"))

@@ -354,3 +354,39 @@ def test_base_converter_reference_case_and_model():
             if Qb // 8 < x < 3 * Qb // 8 or 5 * Qb // 8 < x < 7 * Qb // 8:   # away from the rounding boundary Q/2 (float correction term)
                 centred = x if x < Qb // 2 else x - Qb
                 assert int(ex[j]) == centred % om[0]
+
+
+def test_blind_rotation_schedule_model_matches_oracle():
+    """tools/emulate_br32.py re-executes the re-scheduled blind-rotation kernel of lattice32.cu at thread / register / shared-memory
+    level in numpy (index maps, twiddle indices, padded exchange addresses, carry-free digits, Montgomery reduction, 2^32
+    compensation) and compares with the oracle: the design check that runs without a GPU."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "emulate_br32.py"), "2", "3"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("== oracle") >= 6
+
+
+def test_ternary_blind_rotation_oracle_reduces_to_rotation():
+    """Sanity of the oracle's ternary composition: with BSK+ = RGSW(1) (trivial, noiseless: the gadget rows) and BSK- = RGSW(0) = 0 the
+    step multiplies the accumulator by X^a up to the decomposition's rounding error, and with both keys zero it is the identity."""
+    import numpy as np
+    from oracle import oracle as O
+    q, n = 132120577, 1024
+    ot = O.U32NttTable(10, q); ob = O.ApproxSignedBasis(q, 7, None, 32); lv = ob.decompose_length()
+    rng = np.random.default_rng(9)
+    tv = rng.integers(0, q, n, dtype=np.uint64).astype(np.uint32)
+    zero = np.zeros(2 * 2 * lv * 2 * n, dtype=np.uint32)
+    lwe = np.array([[5, 7, 3]], dtype=np.uint32)
+    acc = O.blind_rotate_ternary(ot, ob, zero, zero, 2, lwe, tv, batch=1)[0]
+    assert np.array_equal(acc[:n], np.zeros(n, np.uint32)) and np.array_equal(acc[n:], O.mul_monomial(tv, 2 * n - 3, q, 32))
+    # trivial RGSW(1): row r, level l, component c = NTT(g_l) if c == r else 0, g_l = 2^(drop + l*beta)
+    plus = np.zeros((2, 2, lv, 2, n), dtype=np.uint32)
+    for i in range(2):
+        for r in range(2):
+            for l, g in enumerate(ob.scalars()):
+                plus[i, r, l, r, :] = g % q      # NTT of the constant polynomial g is the constant vector g
+    acc = O.blind_rotate_ternary(ot, ob, plus.reshape(-1), zero, 2, lwe, tv, batch=1)[0]
+    want = O.mul_monomial(tv, (2 * n - 3 + 5 + 7) % (2 * n), q, 32).astype(np.int64)
+    err = (acc[n:].astype(np.int64) - want + q // 2) % q - q // 2
+    assert np.abs(err).max() <= 2 * (1 << ob.drop_bits())      # two steps, each within the gadget's rounding error

@@ -21,6 +21,10 @@ if which == "br":
     acc = torch.empty((nb, 2 * n), dtype=torch.int32, device="cuda")
     ms = timeit(lambda: t.blind_rotate_batch(7, None, bsk, n_lwe, lwe, tv, acc), reps=int(os.environ.get("REPS", "3")))
     print(f"blind rotate u32 N=1024 n={n_lwe} batch={nb}: {nb/ms*1e3:.4e} bootstraps/s ({ms:.2f} ms)")
+    if os.environ.get("TERNARY"):
+        bsk2 = torch.randint(0, q, (n_lwe * 2 * lv * 2 * n,), dtype=torch.int64, device="cuda").to(torch.int32)
+        ms = timeit(lambda: t.blind_rotate_ternary_batch(7, None, bsk, bsk2, n_lwe, lwe, tv, acc), reps=3)
+        print(f"ternary blind rotate u32 N=1024 n={n_lwe} batch={nb}: {nb/ms*1e3:.4e} bootstraps/s ({ms:.2f} ms)")
 else:
     for bits, q in ((32, 132120577), (64, 1125899906826241)):
         t = (P.U64NttTable if bits == 64 else P.U32NttTable)(11, q); n = 2048
