@@ -24,8 +24,19 @@ namespace pfhe {
 
 std::atomic<uint64_t> g_launches{0};
 
+static int env_int_early(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// experiment hook: PFHE_BIGN_LOGE=4 lays the u64 N = 8192 / 16384 tables out for 16-word register tiles (twice the threads)
+static int bign_loge() {
+    static const int v = env_int_early("PFHE_BIGN_LOGE", 5);
+    return v == 4 ? 4 : 5;
+}
 int choose_loge(int bits, int log_n) {
     if (bits == 64) {
+        if (log_n == 13 || log_n == 14) return bign_loge();
         switch (log_n) {
             case 10: return 5;
             case 11: return 4;
@@ -84,6 +95,7 @@ template <typename F, int LOGN, int LOGE, int PPB> constexpr int ntt_min_blocks(
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     if (sizeof(typename F::WordT) == 8 && LOGN == 12 && LOGE == 4 && PPB == 1)
         return sizeof(typename F::Elem) == 8 && !std::is_integral<typename F::Elem>::value ? 4 : 3;  // FP64: 64 regs x 4 CTAs; int: 80 x 3
+    if (sizeof(typename F::WordT) == 8 && LOGN == 13 && LOGE == 4) return 2;  // 512 threads x 64 registers, two CTAs per SM
     return threads >= 512 ? 1 : 512 / threads;  // at least 16 warps per SM: cap the allocator at 128 registers
 }
 
@@ -304,6 +316,111 @@ polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const 
     if (active && t == 0) tma_store_poly(&out_map, sm, (uint32_t)(poly * Core::kTmaRows), Core::kTmaBoxes, Core::kTmaBoxRows);
 }
 
+// ---- persistent forward kernel for the one-polynomial-per-SM sizes (u64, N = 8192 / 16384) ------------------------------------------
+// At N = 16384 the register file holds exactly one polynomial (512 threads x 32 doubles) and shared memory one exchange buffer, so
+// with one CTA per polynomial the load, FP64 and store/exit phases of an SM never overlap (ncu, profiles/r02_ncu_ntt_fwd_n16384.txt:
+// FP64 pipe 57 % busy, 24 % of the stall samples wait for the loads, 17 % sit at EXIT).  Here a CTA is persistent and the NEXT
+// polynomial is prefetched by bulk TMA copies into a staging buffer `in` while the current one is being transformed:
+//   shared memory = in[N] (raw words of the next polynomial) + xb[N/2] -- 192 KiB at N = 16384;
+//   both exchanges use xb for the lower half of the index space and the FIRST half of `in` for the upper half; the staging buffer is
+//   free between the pass-0 loads and the prefetch, which therefore comes in two pieces: the second half right after the pass-0
+//   loads, the first half after the loads of exchange 2 (it lands while pass 2 runs and the results are stored);
+//   outputs go from registers to HBM as 128-bit streaming stores (each thread owns 256 contiguous bytes).
+template <typename F, int LOGN, int LOGE>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)), (LOGN <= 13 ? 2 : 1))
+ntt_persist_fwd_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
+                       const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
+    using Core = NttCore<F, LOGN, LOGE>;
+    using P = typename Core::P;
+    using T = typename F::WordT;
+    using Elem = typename F::Elem;
+    static_assert(sizeof(T) == 8 && P::NPASS == 3 && LOGE == 5, "built for u64 words, three register passes of 2^5 words");
+    constexpr int N = Core::N, E = Core::E, HALF = N / 2, CW = Core::CW;
+    constexpr int FB0 = P::fb(0), FB1 = P::fb(1);
+    constexpr uint32_t kHalfBytes = sizeof(T) * HALF;
+    extern __shared__ __align__(1024) unsigned char smem_p[];
+    T *in = reinterpret_cast<T *>(smem_p);                        // [N] raw words of the polynomial being (pre)fetched
+    Elem *inx = reinterpret_cast<Elem *>(smem_p);                 // its first half doubles as the upper half of the exchange buffer
+    Elem *xb = reinterpret_cast<Elem *>(smem_p + sizeof(T) * N);  // [N/2] lower half of the exchange buffer
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_p + sizeof(T) * (N + HALF));
+    const int t = threadIdx.x;
+    const int half = t >> (LOGN - LOGE - 1);                      // which half of the index space this thread owns from pass 1 on
+    size_t poly = blockIdx.x;
+    if (poly >= npolys) return;
+    auto copy_half = [&](const T *g, int which) {  // elected thread: 64 KiB (N = 16384) from HBM into one half of the staging buffer
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(in + which * HALF)),
+                     "l"(g + which * HALF), "r"(kHalfBytes), "r"(smem_addr(bar))
+                     : "memory");
+    };
+    auto expect_poly = [&]() {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(2u * kHalfBytes) : "memory");
+    };
+    if (t == 0) {
+        mbar_init(bar, 1);
+        expect_poly();
+        copy_half(src + poly * N, 0);
+        copy_half(src + poly * N, 1);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (; poly < npolys; poly += gridDim.x) {
+        DevNtt<T> tb_copy;
+        if (limbs > 1) tb_copy = tables[poly % (size_t)limbs];
+        const DevNtt<T> &tb = limbs > 1 ? tb_copy : tb0;
+        const typename F::Ctx c = F::ctx(tb);
+        const size_t next = poly + gridDim.x;
+        Elem x[E];
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = F::load(in[Core::elem_index(FB0, t, j)], c);
+        __syncthreads();  // every thread holds its words: the staging buffer is free
+        if (t == 0 && next < npolys) {
+            fence_async_smem();
+            expect_poly();
+            copy_half(src + next * N, 1);  // the half the exchanges never touch
+        }
+        Core::template fwd_pass_regs<0>(x, tb, c, t);
+        // exchange 1 (bit LOGN-1 of the index is bit LOGE-1 of j on the storing side, a thread bit on the loading side)
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+            Elem *buf = (j >> (LOGE - 1)) ? inx : xb;
+            buf[Core::swz(Core::elem_index(FB0, t, j) & (HALF - 1))] = x[j];
+        }
+        __syncthreads();
+        Elem *mine = half ? inx : xb;
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = mine[Core::swz(Core::elem_index(FB1, t, j) & (HALF - 1))];
+        Core::template fwd_pass_regs<1>(x, tb, c, t);
+        // exchange 2: a thread stores to the slots it loaded from, so no barrier is needed in between
+#pragma unroll
+        for (int j = 0; j < E; j++) mine[Core::swz(Core::elem_index(FB1, t, j) & (HALF - 1))] = x[j];
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < E / CW; v++) {
+            const typename Core::Vec w = *reinterpret_cast<const typename Core::Vec *>(mine + Core::swz(((t * E) & (HALF - 1)) + v * CW));
+#pragma unroll
+            for (int k = 0; k < CW; k++) x[v * CW + k] = w.v[k];
+        }
+        __syncthreads();  // exchange buffers are free: the first half of the next polynomial may land
+        if (t == 0 && next < npolys) {
+            fence_async_smem();
+            copy_half(src + next * N, 0);
+        }
+        Core::template fwd_pass_regs<2>(x, tb, c, t);
+        // canonical words straight to HBM: this thread's 2^LOGE contiguous output words
+        T *o = dst + poly * N + (size_t)t * E;
+#pragma unroll
+        for (int v = 0; v < E / CW; v++) {
+            typename Core::WVec w;
+#pragma unroll
+            for (int k = 0; k < CW; k++) w.v[k] = F::fwd_word(x[v * CW + k], c);
+            stg_stream(reinterpret_cast<uint4 *>(o + v * CW), *reinterpret_cast<const uint4 *>(&w));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic radix-2 kernel: any 1 <= log_n that fits shared memory (sizes without a register-pass
 // instantiation, e.g. the reference's small round-trip tests N = 8..512)
@@ -477,6 +594,26 @@ static cudaError_t run_ntt_f(const DevNtt<typename F::WordT> &tb0, const DevNtt<
     // tensor copies: every direction where a thread row is 128 bytes; forward only for 256-byte rows (measured: +4..9 %
     // forward, but the 2-way conflicted row pattern costs the inverse and the fused product more than the copy-out saves)
     constexpr bool kRow128 = sizeof(T) * (1 << LOGE) == 128;
+    if constexpr (sizeof(T) == 8 && LOGE == 5 && LOGN >= 13 && PPB == 1) {
+        static const int persist = env_int("PFHE_NTT_PERSIST", 0);  // experiment, off: measured 8.2 M vs 9.2 M NTT/s at N = 16384 (profiles/r02_large_n_experiments.md)
+        // in place is fine: a CTA only ever prefetches polynomials it will itself overwrite later
+        if (fwd && persist && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            auto k = ntt_persist_fwd_kernel<F, LOGN, LOGE>;
+            constexpr size_t bytes = sizeof(T) * (((size_t)1 << LOGN) + ((size_t)1 << (LOGN - 1))) + 64;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, bytes);
+            if (per_sm < 1) per_sm = 1;
+            const size_t slots = (size_t)sms * per_sm;
+            const unsigned g = (unsigned)(npolys < slots ? npolys : slots);
+            k<<<g, threads, bytes, stream>>>(tb0, tables, limbs, src, dst, npolys);
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     {
         static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;  // A/B tuning hook
         IoMaps maps;
@@ -522,21 +659,7 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
     const unsigned grid = (unsigned)((npolys + PPB - 1) / PPB);
     cudaError_t e;
-    if constexpr (sizeof(T) * (1 << LOGE) == 128) {
-        static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;
-        CUtensorMap map;
-        if (use_tma && make_poly_map<T>(&map, c, npolys, LOGN)) {
-            auto launch = [&](auto k) -> cudaError_t {
-                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-                k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, npolys, map);
-                count_launch();
-                return cudaGetLastError();
-            };
-            if (limbs > 1) return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, true>);
-            return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, false>);
-        }
-    }
-    if constexpr (sizeof(T) == 8 && LOGE == 5 && LOGN >= 13 && PPB == 1) {
+    if constexpr (sizeof(T) == 8 && LOGN >= 13 && PPB == 1) {
         static const bool use_stash = env_int("PFHE_POLYMUL_STASH", 1) != 0;  // A/B tuning hook
         if (c == b) {  // the stash would overwrite b before it is read: the product commutes
             const T *tmp = a;
@@ -549,6 +672,20 @@ static cudaError_t run_polymul_f(const DevNtt<typename F::WordT> &tb0, const Dev
             ks<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, c, npolys);
             count_launch();
             return cudaGetLastError();
+        }
+    }
+    if constexpr (sizeof(T) * (1 << LOGE) == 128 && !(sizeof(T) == 8 && LOGN >= 13)) {
+        static const bool use_tma = env_int("PFHE_NTT_TMA", 1) != 0;
+        CUtensorMap map;
+        if (use_tma && make_poly_map<T>(&map, c, npolys, LOGN)) {
+            auto launch = [&](auto k) -> cudaError_t {
+                if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                k<<<grid, threads, smem, stream>>>(tb0, tables, limbs, a, b, npolys, map);
+                count_launch();
+                return cudaGetLastError();
+            };
+            if (limbs > 1) return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, true>);
+            return launch(polymul_tma_kernel<F, LOGN, LOGE, PPB, false>);
         }
     }
     auto k = polymul_kernel<F, LOGN, LOGE, PPB>;
@@ -609,8 +746,10 @@ cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint6
             case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 11: return run_ntt<T, 11, 4, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 12: return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-            case 13: return run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-            case 14: return run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 13: return tb0.loge == 4 ? run_ntt<T, 13, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s)
+                                          : run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 14: return tb0.loge == 4 ? run_ntt<T, 14, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s)
+                                          : run_ntt<T, 14, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
         }
     }
     return run_generic<T>(tb0, tables, limbs, src, dst, npolys, fwd, s);
@@ -655,8 +794,10 @@ cudaError_t launch_polymul<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<u
             case 10: return run_polymul<T, 10, 5, 4>(tb0, tables, limbs, a, b, c, npolys, s);
             case 11: return run_polymul<T, 11, 4, 2>(tb0, tables, limbs, a, b, c, npolys, s);
             case 12: return run_polymul<T, 12, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s);
-            case 13: return run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
-            case 14: return run_polymul<T, 14, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 13: return tb0.loge == 4 ? run_polymul<T, 13, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s)
+                                          : run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 14: return tb0.loge == 4 ? run_polymul<T, 14, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s)
+                                          : run_polymul<T, 14, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
         }
     }
     return run_polymul_generic<T>(tb0, tables, limbs, a, b, c, npolys, s);
