@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) rns_lift_scaled_acc_kernel(const __grid_c
         for (int l = 0; l < lc.limbs; l++) {
             const T centred = (lc.unsigned_mode || v < lc.half) ? v : lc.temp[l] + v;
             const size_t o = (size_t)l * count + i;
-            acc[o] = mod_add<T>(acc[o], shoup<T>(centred, lc.f[l], lc.fq[l], lc.q[l]), lc.q[l]);
+            acc[o] = mod_add<T>(acc[o], shoup_exact<T>(centred, lc.f[l], lc.fq[l], lc.q[l]), lc.q[l]);  // q may be as large as 2^63 - 1 here
         }
     }
 }
