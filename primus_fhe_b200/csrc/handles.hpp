@@ -1,8 +1,12 @@
 // handles.hpp -- shared by the C-ABI translation units (capi.cu, capi_ext.cu): handle layouts, device guard, per-thread
 // copy streams and the pipelined host <-> device driver of the host-slice shims.
 #pragma once
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_math.hpp"
@@ -57,7 +61,29 @@ struct ThreadStreams {
     struct PerDevice {
         std::vector<cudaStream_t> streams;
         cudaMemPool_t pool = nullptr;
+        void *pin[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned bounce buffers of the pageable-memory path (one per pipeline slot)
+        size_t pin_bytes[4] = {0, 0, 0, 0};
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     };
+    // pinned bounce buffer of slot `i` with at least `bytes` (grown on demand, kept for the life of the thread)
+    cudaError_t staging(int device, int i, size_t bytes, void **out, cudaEvent_t *ev) {
+        auto &d = per_device[device];
+        if (d.pin_bytes[i] < bytes) {
+            if (d.pin[i]) cudaFreeHost(d.pin[i]);
+            d.pin[i] = nullptr;
+            d.pin_bytes[i] = 0;
+            cudaError_t e = cudaHostAlloc(&d.pin[i], bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            d.pin_bytes[i] = bytes;
+        }
+        if (!d.ev[i]) {
+            cudaError_t e = cudaEventCreateWithFlags(&d.ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        *out = d.pin[i];
+        *ev = d.ev[i];
+        return cudaSuccess;
+    }
     std::vector<PerDevice> per_device;
     cudaError_t get(int device, cudaStream_t *out, cudaMemPool_t *pool = nullptr) {
         if ((int)per_device.size() <= device) per_device.resize(device + 1);
@@ -106,6 +132,133 @@ template <typename T> struct DcrtHandle {
     DevNtt<T> tb0{};                // limb 0 by value (same field-policy flag as the device array)
 };
 
+inline bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (!p) return false;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;  // old runtimes report plain malloc memory as an error
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Staged variant of pipelined() for pageable host memory; same chunk / region layout on the device.
+template <typename LaunchF>
+inline pfhe_status pipelined_staged(int device, const void *const *host_in, int n_in, const size_t *in_bytes, void *host_out, size_t out_bytes,
+                                    size_t units, LaunchF launch, int out_alias, size_t scratch_bytes, size_t chunk, int nbuf, size_t per_unit,
+                                    cudaStream_t *st, cudaMemPool_t pool) {
+    const size_t nchunks = (units + chunk - 1) / chunk;
+    int nthreads = 4;
+    if (const char *e = getenv("PFHE_STAGE_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) nthreads = v;
+    }
+    // pinned layout per slot: [input 0][input 1]...[output] (the output aliases input `out_alias` when the kernel works in place)
+    size_t pin_off[5] = {0, 0, 0, 0, 0}, pin_total = 0;
+    for (int i = 0; i < n_in; i++) {
+        pin_off[i] = pin_total;
+        pin_total += (chunk * in_bytes[i] + 255) & ~(size_t)255;
+    }
+    const size_t pin_out_off = out_alias >= 0 ? pin_off[out_alias] : pin_total;
+    if (out_alias < 0) pin_total += (chunk * out_bytes + 255) & ~(size_t)255;
+    void *pin[kPipe] = {};
+    cudaEvent_t ev[kPipe] = {};
+    void *dbuf[kPipe] = {};
+    pfhe_status status = PFHE_OK;
+    for (int i = 0; i < nbuf && status == PFHE_OK; i++) {
+        cudaError_t e = t_streams.staging(device, i, pin_total, &pin[i], &ev[i]);
+        if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit + 6 * 256, pool, st[i]);
+        if (e != cudaSuccess) status = cuda_fail(e);
+    }
+    std::unique_ptr<std::atomic<int>[]> in_ready(new std::atomic<int>[nchunks]), out_done(new std::atomic<int>[nchunks]),
+        launched(new std::atomic<int>[nchunks]);
+    for (size_t c = 0; c < nchunks; c++) {
+        in_ready[c].store(0);
+        out_done[c].store(0);
+        launched[c].store(0);
+    }
+    std::atomic<int> abort_flag{0};
+    auto slice = [&](size_t bytes, int k, size_t &b, size_t &e) {  // 64-byte aligned share k of nthreads
+        const size_t per = ((bytes / nthreads) + 63) & ~(size_t)63;
+        b = per * k < bytes ? per * k : bytes;
+        e = (k == nthreads - 1) ? bytes : (b + per < bytes ? b + per : bytes);
+    };
+    auto units_of = [&](size_t c) { return c + 1 < nchunks ? chunk : units - c * chunk; };
+    std::vector<std::thread> workers;
+    if (status == PFHE_OK) {
+        for (int k = 0; k < nthreads; k++) {
+            workers.emplace_back([&, k] {  // caller memory -> pinned
+                for (size_t c = 0; c < nchunks && !abort_flag.load(); c++) {
+                    const int b = (int)(c % nbuf);
+                    if (c >= (size_t)nbuf)
+                        while (out_done[c - nbuf].load(std::memory_order_acquire) < nthreads && !abort_flag.load()) std::this_thread::yield();
+                    const size_t nu = units_of(c);
+                    for (int i = 0; i < n_in; i++) {
+                        size_t sb, se;
+                        slice(nu * in_bytes[i], k, sb, se);
+                        if (se > sb)
+                            memcpy(static_cast<unsigned char *>(pin[b]) + pin_off[i] + sb,
+                                   static_cast<const unsigned char *>(host_in[i]) + c * chunk * in_bytes[i] + sb, se - sb);
+                    }
+                    in_ready[c].fetch_add(1, std::memory_order_release);
+                }
+            });
+            workers.emplace_back([&, k] {  // pinned -> caller memory
+                cudaSetDevice(device);
+                for (size_t c = 0; c < nchunks && !abort_flag.load(); c++) {
+                    const int b = (int)(c % nbuf);
+                    while (!launched[c].load(std::memory_order_acquire) && !abort_flag.load()) std::this_thread::yield();
+                    if (abort_flag.load()) break;
+                    if (cudaEventSynchronize(ev[b]) != cudaSuccess) {
+                        abort_flag.store(1);
+                        break;
+                    }
+                    size_t sb, se;
+                    slice(units_of(c) * out_bytes, k, sb, se);
+                    if (se > sb)
+                        memcpy(static_cast<unsigned char *>(host_out) + c * chunk * out_bytes + sb,
+                               static_cast<const unsigned char *>(pin[b]) + pin_out_off + sb, se - sb);
+                    out_done[c].fetch_add(1, std::memory_order_release);
+                }
+            });
+        }
+        for (size_t c = 0; c < nchunks; c++) {
+            const int b = (int)(c % nbuf);
+            const size_t nu = units_of(c);
+            while (in_ready[c].load(std::memory_order_acquire) < nthreads && !abort_flag.load()) std::this_thread::yield();
+            if (abort_flag.load()) break;
+            unsigned char *base = static_cast<unsigned char *>(dbuf[b]);
+            const void *din[4] = {nullptr, nullptr, nullptr, nullptr};
+            size_t off = 0;
+            cudaError_t e = cudaSuccess;
+            for (int i = 0; i < n_in && e == cudaSuccess; i++) {
+                din[i] = base + off;
+                e = cudaMemcpyAsync(base + off, static_cast<const unsigned char *>(pin[b]) + pin_off[i], nu * in_bytes[i], cudaMemcpyHostToDevice, st[b]);
+                off += (chunk * in_bytes[i] + 255) & ~(size_t)255;
+            }
+            void *dout = out_alias >= 0 ? const_cast<void *>(din[out_alias]) : static_cast<void *>(base + off);
+            if (scratch_bytes && n_in < 4) din[n_in] = base + off + (out_alias >= 0 ? 0 : ((chunk * out_bytes + 255) & ~(size_t)255));
+            if (e == cudaSuccess) e = launch(din, dout, nu, st[b]);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<unsigned char *>(pin[b]) + pin_out_off, dout, nu * out_bytes, cudaMemcpyDeviceToHost, st[b]);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], st[b]);
+            if (e != cudaSuccess) {
+                status = cuda_fail(e);
+                abort_flag.store(1);
+                break;
+            }
+            launched[c].store(1, std::memory_order_release);
+        }
+        for (auto &w : workers) w.join();
+        if (abort_flag.load() && status == PFHE_OK) status = PFHE_ERR_CUDA;
+    }
+    for (int i = 0; i < nbuf; i++) {
+        if (dbuf[i]) cudaFreeAsync(dbuf[i], st[i]);
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (e != cudaSuccess && status == PFHE_OK) status = cuda_fail(e);
+    }
+    return status;
+}
+
 // Pipelined host <-> device processing of `units` independent work items (`in_bytes`/`out_bytes` each).
 // launch(dev_in_chunks[], dev_out, n_units, stream).
 template <typename LaunchF>
@@ -125,12 +278,27 @@ inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
         const long mb = atol(e);
         if (mb > 0 && mb <= 1024) chunk_bytes = (size_t)mb << 20;
     }
+    // Pageable host memory (what a Rust `&mut [T]` / Vec is): cudaMemcpyAsync would stage it synchronously through the driver's own
+    // bounce buffer (measured 14 GB/s per direction against 46 GB/s pinned).  Large pageable calls are staged here instead: copy
+    // threads move slices between the caller's memory and pinned bounce buffers while the DMA engines and the kernels work on other
+    // chunks.  PFHE_STAGE=0 disables it, PFHE_STAGE_THREADS sets the copy threads per direction (default 4).
+    size_t host_total = out_bytes * units;
+    for (int i = 0; i < n_in; i++) host_total += in_bytes[i] * units;
+    bool staged = false;
+    if (host_total >= ((size_t)8 << 20)) {
+        static const bool stage_on = !(getenv("PFHE_STAGE") && getenv("PFHE_STAGE")[0] == '0');
+        bool pageable = host_is_pageable(host_out);
+        for (int i = 0; i < n_in; i++) pageable = pageable || host_is_pageable(host_in[i]);
+        staged = stage_on && pageable;
+        if (staged && !getenv("PFHE_PIPE_CHUNK_MB")) chunk_bytes = (size_t)32 << 20;
+    }
     size_t chunk = chunk_bytes / (per_unit ? per_unit : 1);
     if (chunk == 0) chunk = 1;
     if (chunk > units) chunk = units;
     const int nbuf = (int)((units + chunk - 1) / chunk < (size_t)kPipe ? (units + chunk - 1) / chunk : kPipe);
     void *dbuf[kPipe] = {};
     pfhe_status status = PFHE_OK;
+    if (staged) return pipelined_staged(device, host_in, n_in, in_bytes, host_out, out_bytes, units, launch, out_alias, scratch_bytes, chunk, nbuf, per_unit, st, pool);
     for (int i = 0; i < nbuf; i++) {
         cudaError_t e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit + 6 * 256, pool, st[i]);  // + alignment slack of the regions
         if (e != cudaSuccess) {
