@@ -15,7 +15,7 @@
 namespace pfhe {
 
 thread_local std::string t_last_cuda_error;
-thread_local ThreadStreams t_streams;
+StreamPool g_stream_pool;
 
 template <typename T>
 static void fill_pass_tables(const host::HostTables<T> &h, int loge, std::vector<typename Word<T>::Pair> &fwd,
@@ -218,11 +218,12 @@ template <typename T> static pfhe_status host_monomial(const NttHandle<T> *t, T 
     if (degree >= 2 * t->h.n || coeff >= t->h.q) return PFHE_ERR_INVALID_ARG;
     DeviceGuard guard(t->device);
     if (!guard.ok) return PFHE_ERR_CUDA;
-    cudaStream_t st[kPipe];
-    PFHE_CUDA(t_streams.get(t->device, st));
+    StreamLease lease(t->device);
+    PFHE_CUDA(lease.err);
+    cudaStream_t *st = lease.ctx->streams;
     const size_t bytes = sizeof(T) << t->h.log_n;
     void *d = nullptr;
-    PFHE_CUDA(cudaMallocAsync(&d, bytes + 256, st[0]));
+    PFHE_CUDA(cudaMallocFromPoolAsync(&d, bytes + 256, lease.ctx->pool, st[0]));
     uint32_t *ddeg = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(d) + bytes);
     const uint32_t deg32 = (uint32_t)degree;
     cudaError_t e = cudaMemcpyAsync(ddeg, &deg32, sizeof(deg32), cudaMemcpyHostToDevice, st[0]);
@@ -266,6 +267,7 @@ static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *
     LimbConsts<T> lc;
     pfhe_status s = make_limb_consts<T>(moduli, limbs, scalars, op, lc);
     if (s != PFHE_OK) return s;
+    PFHE_PTR_GUARD(out);
     PFHE_CUDA(launch_slice_op<T>(op, lc, (int)limbs, a, b, c, out, rows, n, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
@@ -273,6 +275,7 @@ static pfhe_status slice_op_dev(int op, const T *moduli, size_t limbs, const T *
 }  // namespace pfhe
 
 using namespace pfhe;
+
 
 template <typename T> struct RnsHandle {
     std::vector<T> moduli;
@@ -399,6 +402,7 @@ static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t
     if (!make_gadget<T>(t->h.q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;
     if (t->dev_lat.loge == 0 || k < 1 || k > 2) return PFHE_ERR_UNSUPPORTED;
     DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
     PFHE_CUDA(launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
@@ -414,8 +418,6 @@ pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t l
     if (batch == 0) return PFHE_OK;
     DeviceGuard guard(t->device);
     if (!guard.ok) return PFHE_ERR_CUDA;
-    cudaStream_t st[kPipe];
-    PFHE_CUDA(t_streams.get(t->device, st));
     const size_t n = t->h.n, comps = (size_t)k + 1;
     const size_t key_bytes = comps * g.levels * comps * n * sizeof(T), ct_bytes = comps * n * sizeof(T);
     void *dkey = nullptr;
@@ -506,6 +508,7 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
     if (!scratch || scratch_bytes < per_ct) return PFHE_ERR_INVALID_ARG;
     const size_t chunk = scratch_bytes / per_ct;
     DeviceGuard guard(t->device);
+    if (!guard.ok) return PFHE_ERR_CUDA;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     T *digits = static_cast<T *>(scratch);
     const size_t glwe_len = comps * L * n;
@@ -596,38 +599,38 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_forward_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, true, static_cast<cudaStream_t>(stream)));                       \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_inverse_batch(const pfhe_ntt##B *t, T *dev, size_t batch, void *stream) {                               \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, dev, dev, batch, false, static_cast<cudaStream_t>(stream)));                      \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_forward_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
         if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, true, static_cast<cudaStream_t>(stream)));                       \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_inverse_batch_to(const pfhe_ntt##B *t, const T *src, T *dst, size_t batch, void *stream) {              \
         if (!t || ((!src || !dst) && batch)) return PFHE_ERR_INVALID_ARG;                                                             \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->dev, nullptr, 1, src, dst, batch, false, static_cast<cudaStream_t>(stream)));                      \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_monomial_batch(const pfhe_ntt##B *t, T coeff, const uint32_t *degrees, T *out, size_t batch,            \
                                              void *stream) {                                                                          \
         if (!t || ((!degrees || !out) && batch) || coeff >= t->h.q) return PFHE_ERR_INVALID_ARG;                                      \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_monomial<T>(t->dev, coeff, degrees, out, batch, static_cast<cudaStream_t>(stream)));                         \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_ntt##B##_polymul_batch(const pfhe_ntt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {         \
         if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_polymul<T>(t->dev, nullptr, 1, a, b, c, batch, static_cast<cudaStream_t>(stream)));                          \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -661,21 +664,21 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_forward_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), true,         \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_inverse_batch(const pfhe_dcrt##B *t, T *dev, size_t batch, void *stream) {                             \
         if (!t || (!dev && batch)) return PFHE_ERR_INVALID_ARG;                                                                       \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_ntt<T>(t->tb0, t->d_tables, (int)t->limbs.size(), dev, dev, batch * t->limbs.size(), false,        \
                                 static_cast<cudaStream_t>(stream)));                                                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_dcrt##B##_polymul_batch(const pfhe_dcrt##B *t, const T *a, const T *b, T *c, size_t batch, void *stream) {       \
         if (!t || ((!a || !b || !c) && batch)) return PFHE_ERR_INVALID_ARG;                                                           \
-        DeviceGuard guard(t->device);                                                                                                 \
+        PFHE_DEV_GUARD(t->device);                                                                                                 \
         PFHE_CUDA(launch_polymul<T>(t->tb0, t->d_tables, (int)t->limbs.size(), a, b, c, batch * t->limbs.size(),            \
                                     static_cast<cudaStream_t>(stream)));                                                              \
         return PFHE_OK;                                                                                                               \
@@ -697,6 +700,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         LimbConsts<T> lc;                                                                                                             \
         pfhe_status st = make_limb_consts<T>(moduli, limbs, nullptr, (int)op, lc);                                                    \
         if (st != PFHE_OK) return st;                                                                                                 \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_slice_op<T>((int)op, lc, (int)limbs, a, b, nullptr, out, rows, n, static_cast<cudaStream_t>(stream), group)); \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -706,6 +710,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         pfhe_status st = make_limb_consts<T>(moduli, limbs, nullptr, PFHE_OP_MUL, lc);                                                \
         if (st != PFHE_OK) return st;                                                                                                 \
         if ((!a || !s || !w || !out) && rows * n) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_butterfly_mul<T>(lc, (int)limbs, a, s, w, out, rows, n, static_cast<cudaStream_t>(stream)));                 \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -714,6 +719,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         pfhe_status st = make_limb_consts<T>(&q, 1, nullptr, PFHE_OP_MUL, lc);                                                        \
         if (st != PFHE_OK) return st;                                                                                                 \
         if ((!a || !out) && count) return PFHE_ERR_INVALID_ARG;                                                                       \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_inv_slice<T>(lc.br[0], a, out, count, reinterpret_cast<unsigned long long *>(first_bad),                     \
                                       static_cast<cudaStream_t>(stream)));                                                            \
         return PFHE_OK;                                                                                                               \
@@ -730,6 +736,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         GadgetParams<T> g;                                                                                                            \
         if (!make_gadget<T>(q, log_basis, levels_in, g)) return PFHE_ERR_INVALID_ARG;                                                 \
         if ((!values || !digits) && count) return PFHE_ERR_INVALID_ARG;                                                               \
+        PFHE_PTR_GUARD(digits);                                                                                                       \
         PFHE_CUDA(launch_decompose<T>(g, values, digits, count, static_cast<cudaStream_t>(stream)));                                  \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -739,6 +746,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         if (limbs > (size_t)kMaxLimbs || ((!small || !out) && count)) return PFHE_ERR_INVALID_ARG;                                    \
         for (size_t i = 0; i < limbs; i++)                                                                                            \
             if (moduli[i] <= small_modulus) return PFHE_ERR_INVALID_ARG;                                                              \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_rns_lift<T>(moduli, (int)limbs, small_modulus, small, out, count, static_cast<cudaStream_t>(stream)));       \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -757,12 +765,14 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_extract_lwe##B##_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, void *stream) {                       \
         if ((!rlwe || !lwe) && batch) return PFHE_ERR_INVALID_ARG;                                                                    \
+        PFHE_PTR_GUARD(lwe);                                                                                                          \
         PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, 0, 1, static_cast<cudaStream_t>(stream)));                            \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_extract_lwe##B##_ex_batch(T q, const T *rlwe, T *lwe, size_t n, size_t batch, size_t index, size_t count,        \
                                                void *stream) {                                                                        \
         if (((!rlwe || !lwe) && batch) || count == 0 || index + count > n) return PFHE_ERR_INVALID_ARG;                               \
+        PFHE_PTR_GUARD(lwe);                                                                                                          \
         PFHE_CUDA(launch_extract_lwe<T>(q, rlwe, lwe, n, batch, index, count, static_cast<cudaStream_t>(stream)));                    \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -777,11 +787,13 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     }                                                                                                                                 \
     pfhe_status pfhe_rns##B##_compose_batch(const pfhe_rns##B *r, const T *residues, T *big, size_t count, void *stream) {            \
         if (!r || ((!residues || !big) && count)) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_PTR_GUARD(big);                                                                                                          \
         PFHE_CUDA(launch_rns_compose<T>(r->base, residues, big, count, static_cast<cudaStream_t>(stream)));                           \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_rns##B##_decompose_batch(const pfhe_rns##B *r, const T *big, T *residues, size_t count, void *stream) {          \
         if (!r || ((!residues || !big) && count)) return PFHE_ERR_INVALID_ARG;                                                        \
+        PFHE_PTR_GUARD(residues);                                                                                                     \
         PFHE_CUDA(launch_rns_decompose<T>(r->base, big, residues, count, static_cast<cudaStream_t>(stream)));                         \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -792,6 +804,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         for (size_t i = 0; i < limbs; i++)                                                                                            \
             if (moduli[i] <= small_modulus || scalars[i] >= moduli[i] || (moduli[i] >> (sizeof(T) * 8 - 1)) != 0)                     \
                 return PFHE_ERR_INVALID_ARG;                                                                                          \
+        PFHE_PTR_GUARD(acc);                                                                                                          \
         PFHE_CUDA(launch_rns_lift_scaled_acc<T>(moduli, (int)limbs, small_modulus, scalars, small, acc, count,                        \
                                                 static_cast<cudaStream_t>(stream)));                                                  \
         return PFHE_OK;                                                                                                               \
@@ -812,6 +825,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         if (st != PFHE_OK) return st;                                                                                                 \
         if ((!residues || !digits) && n * polys) return PFHE_ERR_INVALID_ARG;                                                         \
         const size_t L = r->moduli.size();                                                                                            \
+        PFHE_PTR_GUARD(digits);                                                                                                       \
         PFHE_CUDA(launch_rns_gadget<T>(g, residues, digits, n, polys, L * n, (size_t)g.levels * L * n,                                \
                                        static_cast<cudaStream_t>(stream)));                                                           \
         return PFHE_OK;                                                                                                               \
@@ -843,12 +857,14 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
     pfhe_status pfhe_baseconv##B##_fast_convert_batch(const pfhe_baseconv##B *c, const T *in, T *out, size_t n, size_t polys,         \
                                                       void *stream) {                                                                 \
         if (!c || ((!in || !out) && n * polys)) return PFHE_ERR_INVALID_ARG;                                                          \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_baseconv<T>(c->dev, in, out, n, polys, false, static_cast<cudaStream_t>(stream)));                           \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
     pfhe_status pfhe_baseconv##B##_exact_convert_batch(const pfhe_baseconv##B *c, const T *in, T *out, size_t n, size_t polys,        \
                                                        void *stream) {                                                                \
         if (!c || c->dev.n_out != 1 || ((!in || !out) && n * polys)) return PFHE_ERR_INVALID_ARG;                                     \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_baseconv<T>(c->dev, in, out, n, polys, true, static_cast<cudaStream_t>(stream)));                            \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -858,6 +874,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         pfhe_status st = limb_consts_plain<T>(moduli, limbs, lc);                                                                     \
         if (st != PFHE_OK) return st;                                                                                                 \
         if (((!degrees || !in || !out) && batch) || in == out || log_n == 0 || log_n > 20) return PFHE_ERR_INVALID_ARG;               \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_mul_monomial<T>(lc, (int)limbs, degrees, in, out, log_n, batch, static_cast<cudaStream_t>(stream)));         \
         return PFHE_OK;                                                                                                               \
     }                                                                                                                                 \
@@ -866,6 +883,7 @@ uint64_t pfhe_launch_count(void) { return g_launches.load(); }
         pfhe_status st = limb_consts_plain<T>(&q, 1, lc);                                                                             \
         if (st != PFHE_OK) return st;                                                                                                 \
         if ((!a || !b || !out) && rows) return PFHE_ERR_INVALID_ARG;                                                                  \
+        PFHE_PTR_GUARD(out);                                                                                                          \
         PFHE_CUDA(launch_dot_product<T>(lc.br[0], a, b, out, rows, n, static_cast<cudaStream_t>(stream)));                            \
         return PFHE_OK;                                                                                                               \
     }

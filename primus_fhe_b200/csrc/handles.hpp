@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -54,65 +56,99 @@ inline int device_of(const void *p) {
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
 
-// per-thread copy streams (thread safe by construction) and a PRIVATE stream-ordered pool per device for the staging
-// buffers of the host-slice shims (freed staging memory stays in the pool; the process-wide default pool is untouched)
+// Entry points that take device pointers but no handle run on the device that owns the pointer (cudaPointerGetAttributes), not on
+// whatever device happens to be current: a process that drives several GPUs gets INVALID_ARG for a host / foreign pointer instead of
+// an illegal-address fault.  Handle-based entry points switch to the handle's device and report PFHE_ERR_CUDA when that fails.
+#define PFHE_PTR_GUARD(ptr)                                   \
+    const int _pdev = device_of(ptr);                         \
+    if (_pdev < 0) return PFHE_ERR_INVALID_ARG;               \
+    DeviceGuard _pguard(_pdev);                               \
+    if (!_pguard.ok) return PFHE_ERR_CUDA
+#define PFHE_DEV_GUARD(dev)       \
+    DeviceGuard guard(dev);       \
+    if (!guard.ok) return PFHE_ERR_CUDA
+
+// Stream contexts of the host-slice shims: kPipe copy/compute streams, a PRIVATE stream-ordered memory pool for the device staging
+// buffers (the process-wide default pool is untouched), pinned bounce buffers for the pageable-memory path and their events.
+// Contexts live in a process-wide pool keyed by device and are leased for the duration of one call, so concurrent callers (any host
+// thread, including the short-lived worker threads of the multi-device drivers) never share streams and nothing is re-created or
+// leaked per call.
 constexpr int kPipe = 4;  // pipeline depth of the host-slice shims (H2D / kernel / D2H + one slack stage)
-struct ThreadStreams {
-    struct PerDevice {
-        std::vector<cudaStream_t> streams;
-        cudaMemPool_t pool = nullptr;
-        void *pin[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned bounce buffers of the pageable-memory path (one per pipeline slot)
-        size_t pin_bytes[4] = {0, 0, 0, 0};
-        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    };
-    // pinned bounce buffer of slot `i` with at least `bytes` (grown on demand, kept for the life of the thread)
-    cudaError_t staging(int device, int i, size_t bytes, void **out, cudaEvent_t *ev) {
-        auto &d = per_device[device];
-        if (d.pin_bytes[i] < bytes) {
-            if (d.pin[i]) cudaFreeHost(d.pin[i]);
-            d.pin[i] = nullptr;
-            d.pin_bytes[i] = 0;
-            cudaError_t e = cudaHostAlloc(&d.pin[i], bytes, cudaHostAllocDefault);
-            if (e != cudaSuccess) return e;
-            d.pin_bytes[i] = bytes;
+struct StreamCtx {
+    int device = -1;
+    cudaStream_t streams[kPipe] = {};
+    cudaMemPool_t pool = nullptr;
+    void *pin[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    size_t pin_bytes[kPipe] = {0, 0, 0, 0};
+    cudaEvent_t ev[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaError_t init(int dev) {
+        device = dev;
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaError_t e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) return e;
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        for (int i = 0; i < kPipe; i++) {
+            if ((e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
-        if (!d.ev[i]) {
-            cudaError_t e = cudaEventCreateWithFlags(&d.ev[i], cudaEventDisableTiming);
-            if (e != cudaSuccess) return e;
-        }
-        *out = d.pin[i];
-        *ev = d.ev[i];
         return cudaSuccess;
     }
-    std::vector<PerDevice> per_device;
-    cudaError_t get(int device, cudaStream_t *out, cudaMemPool_t *pool = nullptr) {
-        if ((int)per_device.size() <= device) per_device.resize(device + 1);
-        auto &d = per_device[device];
-        if (d.streams.empty()) {
-            cudaMemPoolProps props{};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.handleTypes = cudaMemHandleTypeNone;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = device;
-            cudaError_t e = cudaMemPoolCreate(&d.pool, &props);
+    // pinned bounce buffer of slot `i` with at least `bytes` (grown on demand, kept with the context)
+    cudaError_t staging(int i, size_t bytes, void **out) {
+        if (pin_bytes[i] < bytes) {
+            if (pin[i]) cudaFreeHost(pin[i]);
+            pin[i] = nullptr;
+            pin_bytes[i] = 0;
+            cudaError_t e = cudaHostAlloc(&pin[i], bytes, cudaHostAllocDefault);
             if (e != cudaSuccess) return e;
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            d.streams.resize(kPipe);
-            for (auto &s : d.streams) {
-                e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-                if (e != cudaSuccess) {
-                    d.streams.clear();
-                    return e;
-                }
-            }
+            pin_bytes[i] = bytes;
         }
-        for (int i = 0; i < kPipe; i++) out[i] = d.streams[i];
-        if (pool) *pool = d.pool;
+        *out = pin[i];
         return cudaSuccess;
     }
 };
-extern thread_local ThreadStreams t_streams;
+struct StreamPool {
+    std::mutex mu;
+    std::vector<std::vector<StreamCtx *>> idle;  // per device
+    cudaError_t acquire(int device, StreamCtx **out) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if ((int)idle.size() <= device) idle.resize(device + 1);
+            if (!idle[device].empty()) {
+                *out = idle[device].back();
+                idle[device].pop_back();
+                return cudaSuccess;
+            }
+        }
+        auto *c = new (std::nothrow) StreamCtx();
+        if (!c) return cudaErrorMemoryAllocation;
+        const cudaError_t e = c->init(device);
+        if (e != cudaSuccess) {
+            delete c;  // (streams created so far are abandoned: init only fails when the device is unusable)
+            return e;
+        }
+        *out = c;
+        return cudaSuccess;
+    }
+    void release(StreamCtx *c) {
+        std::lock_guard<std::mutex> lock(mu);
+        idle[c->device].push_back(c);
+    }
+};
+extern StreamPool g_stream_pool;
+struct StreamLease {
+    StreamCtx *ctx = nullptr;
+    cudaError_t err;
+    explicit StreamLease(int device) { err = g_stream_pool.acquire(device, &ctx); }
+    ~StreamLease() {
+        if (ctx) g_stream_pool.release(ctx);
+    }
+};
 
 template <typename T> struct NttHandle {
     int device = 0;
@@ -146,7 +182,9 @@ inline bool host_is_pageable(const void *p) {
 template <typename LaunchF>
 inline pfhe_status pipelined_staged(int device, const void *const *host_in, int n_in, const size_t *in_bytes, void *host_out, size_t out_bytes,
                                     size_t units, LaunchF launch, int out_alias, size_t scratch_bytes, size_t chunk, int nbuf, size_t per_unit,
-                                    cudaStream_t *st, cudaMemPool_t pool) {
+                                    StreamCtx *ctx) {
+    cudaStream_t *st = ctx->streams;
+    cudaMemPool_t pool = ctx->pool;
     const size_t nchunks = (units + chunk - 1) / chunk;
     int nthreads = 4;
     if (const char *e = getenv("PFHE_STAGE_THREADS")) {
@@ -166,7 +204,8 @@ inline pfhe_status pipelined_staged(int device, const void *const *host_in, int 
     void *dbuf[kPipe] = {};
     pfhe_status status = PFHE_OK;
     for (int i = 0; i < nbuf && status == PFHE_OK; i++) {
-        cudaError_t e = t_streams.staging(device, i, pin_total, &pin[i], &ev[i]);
+        cudaError_t e = ctx->staging(i, pin_total, &pin[i]);
+        ev[i] = ctx->ev[i];
         if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit + 6 * 256, pool, st[i]);
         if (e != cudaSuccess) status = cuda_fail(e);
     }
@@ -267,9 +306,10 @@ inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
     if (units == 0) return PFHE_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return PFHE_ERR_CUDA;
-    cudaStream_t st[kPipe];
-    cudaMemPool_t pool = nullptr;
-    PFHE_CUDA(t_streams.get(device, st, &pool));
+    StreamLease lease(device);
+    PFHE_CUDA(lease.err);
+    cudaStream_t *st = lease.ctx->streams;
+    cudaMemPool_t pool = lease.ctx->pool;
     size_t per_unit = (out_alias >= 0 ? 0 : out_bytes) + scratch_bytes;  // out_alias: the kernel updates input region #out_alias in place
     for (int i = 0; i < n_in; i++) per_unit += in_bytes[i];  // scratch_bytes: device-only work area per unit, handed to launch as din[n_in]
     // chunk so that each stage moves ~64 MiB (measured best on PCIe Gen5; PFHE_PIPE_CHUNK_MB overrides); at least one unit
@@ -298,7 +338,7 @@ inline pfhe_status pipelined(int device, const void *const *host_in, int n_in, c
     const int nbuf = (int)((units + chunk - 1) / chunk < (size_t)kPipe ? (units + chunk - 1) / chunk : kPipe);
     void *dbuf[kPipe] = {};
     pfhe_status status = PFHE_OK;
-    if (staged) return pipelined_staged(device, host_in, n_in, in_bytes, host_out, out_bytes, units, launch, out_alias, scratch_bytes, chunk, nbuf, per_unit, st, pool);
+    if (staged) return pipelined_staged(device, host_in, n_in, in_bytes, host_out, out_bytes, units, launch, out_alias, scratch_bytes, chunk, nbuf, per_unit, lease.ctx);
     for (int i = 0; i < nbuf; i++) {
         cudaError_t e = cudaMallocFromPoolAsync(&dbuf[i], chunk * per_unit + 6 * 256, pool, st[i]);  // + alignment slack of the regions
         if (e != cudaSuccess) {

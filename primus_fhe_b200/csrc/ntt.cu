@@ -125,7 +125,7 @@ struct IoMaps {
 template <typename F, int LOGN, int LOGE, int PPB, bool FWD, bool PARAM_TB = false>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ntt_min_blocks<F, LOGN, LOGE, PPB>())
 ntt_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
-           const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
+           const typename F::WordT *src, typename F::WordT *dst, size_t npolys) {  // src may equal dst (in place): no __restrict__
     using Core = NttCore<F, LOGN, LOGE>;
     using T = typename F::WordT;
     using Elem = typename F::Elem;
@@ -281,7 +281,7 @@ ntt_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
 template <typename F, int LOGN, int LOGE, int PPB, bool MULTI>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, polymul_min_blocks<F, LOGN, LOGE, PPB>())
 polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
-                   const typename F::WordT *__restrict__ a, const typename F::WordT *__restrict__ b, size_t npolys,
+                   const typename F::WordT *a, const typename F::WordT *b, size_t npolys,  // the output map may alias a or b
                    const __grid_constant__ CUtensorMap out_map) {
     using Core = NttCore<F, LOGN, LOGE, true>;
     using T = typename F::WordT;
@@ -329,7 +329,7 @@ polymul_tma_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const 
 template <typename F, int LOGN, int LOGE>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)), (LOGN <= 13 ? 2 : 1))
 ntt_persist_fwd_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevNtt<typename F::WordT> *__restrict__ tables, int limbs,
-                       const typename F::WordT *__restrict__ src, typename F::WordT *__restrict__ dst, size_t npolys) {
+                       const typename F::WordT *src, typename F::WordT *dst, size_t npolys) {  // src may equal dst
     using Core = NttCore<F, LOGN, LOGE>;
     using P = typename Core::P;
     using T = typename F::WordT;
@@ -427,7 +427,7 @@ ntt_persist_fwd_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, co
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void ntt_generic_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs,
-                                   const T *__restrict__ src, T *__restrict__ dst, size_t npolys, int forward) {
+                                   const T *src, T *dst, size_t npolys, int forward) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     const size_t poly = blockIdx.x;
@@ -477,7 +477,7 @@ __global__ void ntt_generic_kernel(const __grid_constant__ DevNtt<T> tb0, const 
 
 template <typename T>
 __global__ void polymul_generic_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs,
-                                       const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t npolys) {
+                                       const T *a, const T *b, T *c, size_t npolys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t poly = blockIdx.x;
     const DevNtt<T> tb = pick_table(tb0, tables, limbs, poly);

@@ -45,13 +45,15 @@ template <typename T> __device__ __forceinline__ typename Word<T>::Pair ld_pair(
 
 // Streaming global accesses: polynomial data is touched exactly once per kernel, so it must not evict the twiddle
 // tables from L1 (they are re-read by every polynomial): loads bypass L1 allocation, stores are marked streaming.
+// The loads are ordinary coherent loads (no `.nc`): the transforms run in place (`forward_batch(dev, dev)`), i.e. the
+// kernel writes the memory it reads, which the read-only (non-coherent) path does not allow.
 #ifndef PFHE_STREAM_HINTS
 #define PFHE_STREAM_HINTS 1
 #endif
 __device__ __forceinline__ uint32_t ldg_stream(const uint32_t *p) {
 #if PFHE_STREAM_HINTS
     uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 #else
     return __ldg(p);
@@ -60,7 +62,7 @@ __device__ __forceinline__ uint32_t ldg_stream(const uint32_t *p) {
 __device__ __forceinline__ uint64_t ldg_stream(const uint64_t *p) {
 #if PFHE_STREAM_HINTS
     uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 #else
     return __ldg(p);
@@ -69,7 +71,7 @@ __device__ __forceinline__ uint64_t ldg_stream(const uint64_t *p) {
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 #if PFHE_STREAM_HINTS
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 #else
     return __ldg(p);

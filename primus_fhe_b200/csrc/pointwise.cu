@@ -55,9 +55,9 @@ constexpr bool op_reads_out(int op) { return op == PFHE_OP_ADD_MUL || op == PFHE
 
 // slices are [rows][limbs][n]; vectorised when n % W == 0 (always true for polynomial lengths >= 4)
 template <typename T, int OP, bool VEC>
-__global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, const T *__restrict__ a,
-                                                       const T *__restrict__ b, const T *__restrict__ c, T *out, size_t rows, size_t n,
-                                                       size_t b_group) {
+__global__ void __launch_bounds__(256) slice_op_kernel(const __grid_constant__ LimbConsts<T> lc, int limbs, const T *a, const T *b, const T *c,
+                                                       T *out, size_t rows, size_t n, size_t b_group) {
+    // no __restrict__: the *_assign operators of the reference run in place (out aliases a, b or c)
     // b_group > 1: row r of `a` pairs with row r / b_group of `b` (one polynomial against every component of a ciphertext)
     constexpr int W = VEC ? VecOf<T>::W : 1;
     using V = typename VecOf<T>::type;
