@@ -394,6 +394,17 @@ static pfhe_status slice_op_host(int op, const T *moduli, size_t limbs, const T 
     }, io);
 }
 
+// single-modulus external product: the re-scheduled u32 kernels (lattice32_ep.cu) where they apply, the generic kernel otherwise
+template <typename T, typename H>
+static cudaError_t run_external_product(const H *t, const GadgetParams<T> &g, uint32_t k, const T *key, const T *in, T *out, size_t batch, bool to_coeff,
+                                        cudaStream_t s) {
+    if constexpr (sizeof(T) == 4) {
+        const cudaError_t e = launch_external_product_fast32(t->dev_lat, t->head, g, k, key, in, out, batch, to_coeff, s);
+        if (e != cudaErrorNotSupported) return e;
+    }
+    return launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff, s);
+}
+
 template <typename T, typename H>
 static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t levels_in, const T *key, const T *in, T *out, size_t batch,
                             int to_coeff, void *stream) {
@@ -403,7 +414,7 @@ static pfhe_status ext_prod(const H *t, uint32_t k, uint32_t log_basis, uint32_t
     if (t->dev_lat.loge == 0 || k < 1 || k > 2) return PFHE_ERR_UNSUPPORTED;
     DeviceGuard guard(t->device);
     if (!guard.ok) return PFHE_ERR_CUDA;
-    PFHE_CUDA(launch_external_product<T>(t->dev_lat, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
+    PFHE_CUDA(run_external_product<T>(t, g, k, key, in, out, batch, to_coeff != 0, static_cast<cudaStream_t>(stream)));
     return PFHE_OK;
 }
 // Host-slice shim of the single-modulus external product: key uploaded once, ciphertexts streamed through the pipelined
@@ -428,8 +439,8 @@ pfhe_status ext_prod_host(const H *t, uint32_t k, uint32_t log_basis, uint32_t l
         const void *ins[1] = {in};
         const size_t inb[1] = {ct_bytes};
         status = pipelined(t->device, ins, 1, inb, out, ct_bytes, batch, [&](const void *const *din, void *dout, size_t nu, cudaStream_t s) {
-            return launch_external_product<T>(t->dev_lat, g, k, static_cast<const T *>(dkey), static_cast<const T *>(din[0]),
-                                              static_cast<T *>(dout), nu, to_coeff != 0, s);
+            return run_external_product<T>(t, g, k, static_cast<const T *>(dkey), static_cast<const T *>(din[0]), static_cast<T *>(dout), nu,
+                                           to_coeff != 0, s);
         });
     }
     cudaFree(dkey);

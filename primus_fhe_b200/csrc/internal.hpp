@@ -73,6 +73,10 @@ template <typename T> struct LatHead {
 cudaError_t launch_blind_rotate_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
                                        const uint32_t *bsk, uint32_t n_lwe, const uint32_t *lwe, const uint32_t *test_vector,
                                        uint32_t *acc_out, size_t batch, cudaStream_t stream);
+// k = 1 external product, u32, N = 1024 / 2048 (lattice32_ep.cu); cudaErrorNotSupported when (table, gadget) does not qualify
+cudaError_t launch_external_product_fast32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g, uint32_t k,
+                                           const uint32_t *key, const uint32_t *in, uint32_t *out, size_t batch, bool to_coeff,
+                                           cudaStream_t stream);
 // ternary-secret (monomial-combination) blind rotation, same shape restrictions
 cudaError_t launch_blind_rotate_ternary32(const DevNtt<uint32_t> &tb, const LatHead<uint32_t> &head, const GadgetParams<uint32_t> &g,
                                           const uint32_t *bsk_plus, const uint32_t *bsk_minus, uint32_t n_lwe, const uint32_t *lwe,

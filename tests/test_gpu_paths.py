@@ -52,6 +52,15 @@ for bits, q in ((32, 132120577), (64, 1125899906826241)):
     key_ = torch.from_numpy(rng.integers(0, q, 2 * lv * 2 * 1024, dtype=np.uint64).astype(np.int64)).to(tdt).cuda()
     cin = torch.from_numpy(rng.integers(0, q, (4, 2048), dtype=np.uint64).astype(np.int64)).to(tdt).cuda()
     o = torch.empty_like(cin); t.external_product_batch(1, 7, None, key_, cin, o, True); out[f"ep{bits}"] = dig(o)
+    o2 = torch.empty_like(cin); t.external_product_batch(1, 7, None, key_, cin, o2, False); out[f"ep{bits}_ntt"] = dig(o2)
+# u32 N = 2048 external product: re-scheduled kernel (lattice32_ep.cu) vs the generic one (PFHE_EP_FAST=0)
+t = P.U32NttTable(11, 132120577)
+for lb, lvl in ((7, None), (4, 5)):
+    lv = P.ApproxSignedBasis(132120577, lb, lvl, 32).decompose_length()
+    key_ = torch.from_numpy(rng.integers(0, 132120577, 2 * lv * 2 * 2048, dtype=np.uint64).astype(np.int64)).to(torch.int32).cuda()
+    cin = torch.from_numpy(rng.integers(0, 132120577, (5, 4096), dtype=np.uint64).astype(np.int64)).to(torch.int32).cuda()
+    for tc in (True, False):
+        o = torch.empty_like(cin); t.external_product_batch(1, lb, lvl, key_, cin, o, tc); out[f"ep32_n2048_b{lb}_{int(tc)}"] = dig(o)
 # blind rotation: re-scheduled u32 kernel (lattice32.cu) vs the generic lattice kernel (PFHE_BR_FAST=0)
 t = P.U32NttTable(10, 132120577)
 for lb, lvl, nl in ((7, None, 24), (4, 5, 8), (1, 6, 8)):
@@ -75,7 +84,8 @@ def _run(env):
 def test_all_kernel_variants_agree_bit_for_bit():
     base = _run({})
     for env in ({"PFHE_NTT_TMA": "0"}, {"PFHE_F64_LAZY": "0"}, {"PFHE_DISABLE_F64": "1"}, {"PFHE_DISABLE_WIDE32": "1"},
-                {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}, {"PFHE_BR_FAST": "0"}, {"PFHE_BR_MINB": "5"}):
+                {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}, {"PFHE_BR_FAST": "0"}, {"PFHE_BR_MINB": "5"}, {"PFHE_EP_FAST": "0"},
+                {"PFHE_POLYMUL_STASH": "0"}, {"PFHE_STAGE": "0"}):
         other = _run(env)
         diff = [k for k in base if base[k] != other[k]]
         assert not diff, (env, diff)

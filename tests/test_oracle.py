@@ -365,6 +365,9 @@ def test_blind_rotation_schedule_model_matches_oracle():
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "emulate_br32.py"), "2", "3"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("== oracle") >= 6
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "emulate_ep32_2048.py"), "5"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr        # N = 2048 schedule of lattice32_ep.cu (3 + 3 + 3 + 2 passes)
+    assert p.stdout.count("== oracle") >= 3
 
 
 def test_ternary_blind_rotation_oracle_reduces_to_rotation():
