@@ -637,6 +637,16 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
         cout = torch.empty_like(cin)
         dt = timed(lambda: t11.external_product_batch(1, 7, None, key, cin, cout, True))
         extra[f"external_products_per_s_n2048_{tag}"] = 4096 / dt
+        if bits == 32:   # C4 instance A: 2l forward + 2 inverse transforms + 4lN multiply-accumulates = 116,736 modular multiplications
+            mm = 2 * lv * 11264 + 4 * lv * 2048 + 2 * (11264 + 1024)
+            pk = modmul_peak(P, local_rank)
+            extra[f"external_product_n2048_{tag}_roofline"] = {"bound": "integer pipe (IMAD)", "modmuls_per_product": mm, "achieved": 4096 / dt * mm,
+                                                               "peak": pk, "unit": "modmul/s", "frac": 4096 / dt * mm / pk,
+                                                               "kernel": "external_product_u32_kernel<N=2048> (lattice32_ep.cu)"}
+        else:            # C4 instance B: FP64-pipe bound (2l + 2 transforms of ~76 K FP64 instructions, 4lN products of ~7)
+            fp = (2 * lv + 2) * (11264 * 8 + 2 * 2048 * 3) + 4 * lv * 2048 * 7
+            extra[f"external_product_n2048_{tag}_roofline"] = {"bound": "fp64 pipe", "fp64_instr_per_product": fp, "frac": 4096 / dt * fp / FP64_PEAK,
+                                                               "peak_instr_per_s": FP64_PEAK, "kernel": "external_product_kernel<F64LazyField> (lattice.cu)"}
         want = O.external_product_single(o11, ob, 1, key.cpu().numpy().view(ndt), cin[:2].cpu().numpy().view(ndt).copy(), to_coeff=True, batch=2, threads=1)
         checks[f"external_product_n2048_{tag}"] = bool(np.array_equal(cout[:2].cpu().numpy().view(ndt), want))
         # end to end through the host-slice shim (key uploaded per call, ciphertexts streamed)
@@ -654,8 +664,11 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
     rb, rc = ra.flip(0).contiguous(), torch.empty_like(ra)
     dt = timed(lambda: dc.polymul_batch(ra, rb, rc))
     extra["rns_polymuls_per_s_n16384_l8_u64"] = nrns / dt
-    extra["rns_polymul_n16384_l8_roofline"] = dict(roof(nrns * 3 * 8 * 16384 * 8 / dt), bound="hbm",
-                                                   algorithmic_bytes_per_product=3 * 8 * 16384 * 8)
+    fp_limb = 3 * (8192 * 14 * 8 + 2 * 16384 * 3 + 16384 * 4) + 16384 * 12   # FP64 instructions of one limb product (3 transforms + pointwise)
+    extra["rns_polymul_n16384_l8_roofline"] = dict(roof(nrns * 3 * 8 * 16384 * 8 / dt), bound="fp64 pipe (binding) / hbm",
+                                                   algorithmic_bytes_per_product=3 * 8 * 16384 * 8, fp64_instr_per_limb_product=fp_limb,
+                                                   frac_of_fp64_pipe=nrns * 8 / dt * fp_limb / FP64_PEAK,
+                                                   note="one polynomial per SM (register file and shared memory full): see profiles/r02_large_n_experiments.md")
     want = np.stack([O.U64NttTable(14, m).polymul_batch(u64(ra[:1, i]).copy(), u64(rb[:1, i]).copy(), 1) for i, m in enumerate(c3)], axis=1)
     checks["rns_polymul_n16384_l8"] = bool(np.array_equal(u64(rc[:1]), want))
     fa = ra.clone()
