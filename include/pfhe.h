@@ -370,7 +370,8 @@ pfhe_status pfhe_rns32_gadget_decompose_batch(const pfhe_rns32 *r, uint32_t log_
  * (glwe/dcrt.rs:108-126; reduce_dot_product, primus_modulus/src/common/compact/slice.rs:371-401) -> optional inverse NTT.
  * key: device [k+1][levels][k+1][limbs][N] NTT domain; in/out: device [batch][k+1][limbs][N].
  * `scratch`: device memory for the digits; any size >= ..._scratch_bytes(batch = 1) works, the batch is processed in
- * chunks that fit (no allocation on the hot path). */
+ * chunks that fit (no allocation on the hot path).  When the composed value Q fits two words (e.g. two 50-bit limbs) the
+ * product runs as ONE kernel with the digits in registers and `scratch` is not touched (it may be NULL). */
 size_t pfhe_dcrt64_external_product_scratch_bytes(const pfhe_dcrt64 *t, const pfhe_rns64 *r, uint32_t k, uint32_t log_basis,
                                                   uint32_t levels_in, size_t batch);
 size_t pfhe_dcrt32_external_product_scratch_bytes(const pfhe_dcrt32 *t, const pfhe_rns32 *r, uint32_t k, uint32_t log_basis,

@@ -515,6 +515,18 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
     if (st != PFHE_OK) return st;
     LimbConsts<T> lc;
     if ((st = limb_consts_plain<T>(r->moduli.data(), L, lc)) != PFHE_OK) return st;
+    static const bool unfused = getenv("PFHE_DCRT_EP_UNFUSED") != nullptr;     // A/B tuning hooks
+    static const bool two_kernel = getenv("PFHE_DCRT_EP_TWO_KERNEL") != nullptr;
+    if (t->d_tables_lat && !unfused && !two_kernel) {  // composed values of at most two words: ONE kernel, no digit round trip, no scratch
+        DeviceGuard fguard(t->device);
+        if (!fguard.ok) return PFHE_ERR_CUDA;
+        const cudaError_t fe = launch_dcrt_external_product_fused<T>(t->lat_policy, t->d_tables_lat, g, t->limbs[0]->h.log_n, k, key, in, out, batch,
+                                                                     to_coeff != 0, static_cast<cudaStream_t>(stream));
+        if (fe != cudaErrorNotSupported) {
+            PFHE_CUDA(fe);
+            return PFHE_OK;
+        }
+    }
     const size_t per_ct = comps * g.levels * L * n * sizeof(T);
     if (!scratch || scratch_bytes < per_ct) return PFHE_ERR_INVALID_ARG;
     const size_t chunk = scratch_bytes / per_ct;
@@ -529,7 +541,6 @@ static pfhe_status dcrt_ext_prod(const D *t, const R *r, uint32_t k, uint32_t lo
         T *cout = out + done * glwe_len;
         // digits of every input component: [ct][r][level][limb][n]
         PFHE_CUDA(launch_rns_gadget<T>(g, cin, digits, n, nb * comps, L * n, (size_t)g.levels * L * n, s));
-        static const bool unfused = getenv("PFHE_DCRT_EP_UNFUSED") != nullptr;  // A/B tuning hook
         if (t->d_tables_lat && !unfused) {  // one fused kernel per (ciphertext, limb): digits read once, nothing written back
             PFHE_CUDA(launch_dcrt_external_product<T>(t->lat_policy, t->d_tables_lat, (int)L, t->limbs[0]->h.log_n, k, g.levels, key, digits,
                                                       cout, nb, to_coeff != 0, s));

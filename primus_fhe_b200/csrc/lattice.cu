@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "internal.hpp"
+#include "rns.hpp"
 
 namespace pfhe {
 
@@ -530,6 +531,215 @@ template cudaError_t launch_dcrt_external_product<uint32_t>(int, const DevNtt<ui
                                                             const uint32_t *, uint32_t *, size_t, bool, cudaStream_t);
 template cudaError_t launch_dcrt_external_product<uint64_t>(int, const DevNtt<uint64_t> *, int, uint32_t, uint32_t, uint32_t, const uint64_t *,
                                                             const uint64_t *, uint64_t *, size_t, bool, cudaStream_t);
+
+// ---- multi-limb external product in ONE kernel (composed values of at most two words) ------------------------------------------------
+// The digits of CrtGlwe::mul_dcrt_ggsw_to couple all limbs of a coefficient (compose -> multi-word gadget,
+// primus_lattice/src/glwe/dcrt.rs:219-236), which is why round 1 wrote them to HBM first (21 % of the product's time, profiles/
+// r02_large_n_experiments.md).  For Q below two words the coupling is cheap enough to repeat per limb: the CTA of (ciphertext, limb)
+// composes its 8 coefficients per thread itself (base.rs:609-636), adds the carry-free digit offset
+//     R = 2^(drop-1) + sum_l (B/2) 2^(drop + l*beta)
+// once per input component -- the balanced digits of init_value_carry_slice_inplace + unsigned_decompose_slice_to + the centred lift
+// (big_integer/basis.rs:326-367, big_integer/common.rs:275-325, base.rs:279-315) are window_l(value + R) - B/2 -- and then runs the
+// same transform / multiply-accumulate / inverse as dcrt_external_product_kernel with the digits produced in registers.
+template <typename T> struct BigGadget {
+    T q[kRnsMaxLimbs];
+    T product[2], punct[kRnsMaxLimbs][2];
+    T inv_punct[kRnsMaxLimbs], inv_punct_q[kRnsMaxLimbs];
+    T threshold[2], add[2], offset[2];  // offset = R
+    T mask, half;
+    uint32_t drop_bits, log_basis, levels;
+    int limbs, has_threshold;
+};
+template <typename T> struct TwoWords;
+template <> struct TwoWords<uint32_t> { using U = uint64_t; };
+template <> struct TwoWords<uint64_t> { using U = unsigned __int128; };
+
+template <typename F, int LOGN, int LOGE, int COMPS, int VLEN>
+__global__ void __launch_bounds__((1 << (LOGN - LOGE)), ep_min_blocks<LOGN, LOGE, 1>())
+dcrt_external_product_fused_kernel(const DevNtt<typename F::WordT> *__restrict__ tables, const __grid_constant__ BigGadget<typename F::WordT> bg,
+                                   const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ in,
+                                   typename F::WordT *__restrict__ out, int to_coeff) {
+    using EP = ExtProd<F, LOGN, LOGE, COMPS>;
+    using Core = typename EP::Core;
+    using T = typename F::WordT;
+    using U = typename TwoWords<T>::U;
+    using Elem = typename F::Elem;
+    using LA = LatAcc<F>;
+    constexpr int N = EP::N, E = EP::E, CW = EP::CW, NV = EP::NV, FB0 = EP::FB0, BITS = sizeof(T) * 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Elem *sm = reinterpret_cast<Elem *>(smem_raw);
+    const int t = threadIdx.x, limbs = bg.limbs;
+    const size_t ct = blockIdx.x / (unsigned)limbs;
+    const int limb = (int)(blockIdx.x % (unsigned)limbs);
+    const DevNtt<T> tb = tables[limb];
+    const typename F::Ctx cx = F::ctx(tb);
+    const T q = tb.q, mask = bg.mask, half = bg.half;
+    const uint32_t levels = bg.levels;
+    const U bigq = VLEN == 2 ? (((U)bg.product[1] << BITS) | bg.product[0]) : (U)bg.product[0];
+    const U thr = VLEN == 2 ? (((U)bg.threshold[1] << BITS) | bg.threshold[0]) : (U)bg.threshold[0];
+    const U addv = VLEN == 2 ? (((U)bg.add[1] << BITS) | bg.add[0]) : (U)bg.add[0];
+    const U offs = VLEN == 2 ? (((U)bg.offset[1] << BITS) | bg.offset[0]) : (U)bg.offset[0];
+    LSyncBlock sync;
+    typename EP::Acc acc[COMPS][E];
+#pragma unroll
+    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+        for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
+    uint32_t terms = 0;
+#pragma unroll 1
+    for (int r = 0; r < COMPS; r++) {
+        // composed coefficient + threshold adjustment + digit offset, 8 per thread
+        U w[E];
+        const T *cin = in + ((ct * COMPS + r) * limbs) * (size_t)N;
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+            const int idx = Core::elem_index(FB0, t, j);
+            U v = 0;
+            for (int i = 0; i < limbs; i++) {
+                const T prod = shoup<T>(__ldg(cin + (size_t)i * N + idx), bg.inv_punct[i], bg.inv_punct_q[i], bg.q[i]);
+                U term = (U)bg.punct[i][0] * prod;                        // (Q / q_i) * prod < Q
+                if (VLEN == 2) term += (U)(T)(bg.punct[i][1] * prod) << BITS;
+                const U s = v + term;
+                v = (s < v || s >= bigq) ? s - bigq : s;                   // one subtraction: both operands are below Q
+            }
+            if (bg.has_threshold && v >= thr) v += addv;
+            w[j] = v + offs;  // a carry out of the top word is beyond every digit window
+        }
+#pragma unroll 1
+        for (uint32_t l = 0; l < levels; l++) {
+            const uint32_t pos = bg.drop_bits + l * bg.log_basis;
+            Elem x[E];
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                const T win = (T)(w[j] >> pos) & mask;
+                const T d = win >= half ? win - half : win + (q - half);   // balanced digit window - B/2, canonical mod q_limb
+                x[j] = F::load(d, cx);
+            }
+            Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
+            if (LA::kRenorm) {
+                if (terms == LA::kRenormEvery) {
+#pragma unroll
+                    for (int c = 0; c < COMPS; c++)
+#pragma unroll
+                        for (int j = 0; j < E; j++) LA::renorm(acc[c][j], cx);
+                    terms = 1;
+                }
+                terms++;
+            }
+#pragma unroll
+            for (int c = 0; c < COMPS; c++) {
+                const T *kp = key + (((((size_t)r * levels + l) * COMPS + c) * limbs + limb) * (size_t)N) + (size_t)t * E;
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const typename Core::WVec kv = ldg_vec(reinterpret_cast<const typename Core::WVec *>(kp) + v);
+#pragma unroll
+                    for (int k = 0; k < CW; k++) LA::mac(acc[c][v * CW + k], x[v * CW + k], kv.v[k], cx);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COMPS; c++) {
+        T *o = out + (((ct * COMPS + c) * limbs + limb) * (size_t)N);
+        Elem x[E];
+        if (to_coeff) {
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::from_mac(LA::final(acc[c][j], cx), cx);
+            Core::template inv_from<Core::P::NPASS - 1>(x, sm, tb, cx, t, sync);
+            Core::inv_regs_to_global(x, o, cx, t);
+            sync();
+        } else {
+#pragma unroll
+            for (int j = 0; j < E; j++) x[j] = F::mac_bits(LA::final(acc[c][j], cx), cx);
+            Core::template sm_store<Core::P::NPASS - 1>(x, sm, t);
+            sync();
+            Core::copy_s2g(sm, o, t);
+            sync();
+        }
+    }
+}
+
+template <typename F, int LOGN, int COMPS, int VLEN>
+static cudaError_t run_dcrt_ep_fused_f(const DevNtt<typename F::WordT> *tables, const BigGadget<typename F::WordT> &bg, const typename F::WordT *key,
+                                       const typename F::WordT *in, typename F::WordT *out, size_t batch, bool to_coeff, cudaStream_t stream) {
+    using T = typename F::WordT;
+    constexpr int threads = 1 << (LOGN - 3);
+    constexpr size_t smem = sizeof(T) * ((size_t)1 << LOGN);
+    auto k = dcrt_external_product_fused_kernel<F, LOGN, 3, COMPS, VLEN>;
+    cudaError_t e;
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<(unsigned)(batch * bg.limbs), threads, smem, stream>>>(tables, bg, key, in, out, to_coeff ? 1 : 0);
+    count_launch();
+    return cudaGetLastError();
+}
+template <typename T, int LOGN, int COMPS, int VLEN>
+static cudaError_t run_dcrt_ep_fused(int policy, const DevNtt<T> *tables, const BigGadget<T> &bg, const T *key, const T *in, T *out, size_t batch,
+                                     bool to_coeff, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 8) {
+        if (policy == 1) return run_dcrt_ep_fused_f<F64LazyField, LOGN, COMPS, VLEN>(tables, bg, key, in, out, batch, to_coeff, stream);
+    } else {
+        if (policy == 2) return run_dcrt_ep_fused_f<IntWide32Field, LOGN, COMPS, VLEN>(tables, bg, key, in, out, batch, to_coeff, stream);
+    }
+    return run_dcrt_ep_fused_f<IntField<T>, LOGN, COMPS, VLEN>(tables, bg, key, in, out, batch, to_coeff, stream);
+}
+
+// cudaErrorNotSupported: composed value longer than two words, k > 2 or a degree without a lattice tile (the caller then uses the
+// gadget kernel + per-limb kernel pair)
+template <typename T>
+cudaError_t launch_dcrt_external_product_fused(int policy, const DevNtt<T> *tables, const RnsDev<T> &r, uint32_t log_n, uint32_t k, const T *key,
+                                               const T *in, T *out, size_t batch, bool to_coeff, cudaStream_t s) {
+    constexpr int BITS = sizeof(T) * 8;
+    if (r.value_len > 2 || r.log_basis == 0 || k < 1 || k > 2 || log_n < 10 || log_n > 12) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    BigGadget<T> bg{};
+    bg.limbs = r.limbs;
+    for (int i = 0; i < r.limbs; i++) {
+        bg.q[i] = r.q[i];
+        bg.punct[i][0] = r.punct[i][0];
+        bg.punct[i][1] = r.value_len > 1 ? r.punct[i][1] : 0;
+        bg.inv_punct[i] = r.inv_punct[i];
+        bg.inv_punct_q[i] = r.inv_punct_q[i];
+    }
+    for (int w = 0; w < 2; w++) {
+        bg.product[w] = w < r.value_len ? r.product[w] : 0;
+        bg.threshold[w] = w < r.value_len ? r.threshold[w] : 0;
+        bg.add[w] = w < r.value_len ? r.add[w] : 0;
+    }
+    bg.has_threshold = r.has_threshold;
+    bg.mask = r.basis_m1;
+    bg.half = r.log_basis == 1 ? 0 : (T)((T)1 << (r.log_basis - 1));
+    bg.drop_bits = r.drop_bits;
+    bg.log_basis = r.log_basis;
+    bg.levels = r.levels;
+    // R = 2^(drop-1) + sum_l half << (drop + l*beta), as two words
+    unsigned __int128 R = r.drop_bits ? (unsigned __int128)1 << (r.drop_bits - 1) : 0;
+    for (uint32_t l = 0; l < r.levels; l++) {
+        const uint32_t pos = r.drop_bits + l * r.log_basis;
+        if (pos < 128) R += (unsigned __int128)bg.half << pos;
+    }
+    bg.offset[0] = (T)R;
+    bg.offset[1] = (T)(R >> BITS);
+    const bool two = r.value_len == 2;
+#define PFHE_DEPF_CASE(LOGN)                                                                                                       \
+    case LOGN:                                                                                                                     \
+        if (k == 1) return two ? run_dcrt_ep_fused<T, LOGN, 2, 2>(policy, tables, bg, key, in, out, batch, to_coeff, s)            \
+                               : run_dcrt_ep_fused<T, LOGN, 2, 1>(policy, tables, bg, key, in, out, batch, to_coeff, s);           \
+        return two ? run_dcrt_ep_fused<T, LOGN, 3, 2>(policy, tables, bg, key, in, out, batch, to_coeff, s)                        \
+                   : run_dcrt_ep_fused<T, LOGN, 3, 1>(policy, tables, bg, key, in, out, batch, to_coeff, s);
+    switch (log_n) {
+        PFHE_DEPF_CASE(10)
+        PFHE_DEPF_CASE(11)
+        PFHE_DEPF_CASE(12)
+    }
+#undef PFHE_DEPF_CASE
+    return cudaErrorNotSupported;
+}
+template cudaError_t launch_dcrt_external_product_fused<uint32_t>(int, const DevNtt<uint32_t> *, const RnsDev<uint32_t> &, uint32_t, uint32_t,
+                                                                  const uint32_t *, const uint32_t *, uint32_t *, size_t, bool, cudaStream_t);
+template cudaError_t launch_dcrt_external_product_fused<uint64_t>(int, const DevNtt<uint64_t> *, const RnsDev<uint64_t> &, uint32_t, uint32_t,
+                                                                  const uint64_t *, const uint64_t *, uint64_t *, size_t, bool, cudaStream_t);
 
 // The lattice kernels use their own (smaller) register tile: DevNtt::fwd_pass/inv_pass must have been laid
 // out for lattice_loge(bits, log_n) -- capi.cu passes the matching DevNtt view.

@@ -187,6 +187,7 @@ polymul_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb0, const DevN
         static_assert(PPB == 1, "the stash variant runs one polynomial per CTA");
         T *g_c = cc + poly * N;
         Elem x[E];
+        // (a bulk L2 prefetch of b at this point -- cp.async.bulk.prefetch.L2 -- was measured: 2.19 M against 2.78 M limb products/s)
         Core::forward_g2r(a + poly * N, x, sm, tb, c, t, sync);
         Core::fwd_regs_to_sm(x, sm, c, t);
         sync();

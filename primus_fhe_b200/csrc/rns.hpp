@@ -51,6 +51,10 @@ cudaError_t launch_rns_lift_scaled_acc(const T *moduli, int limbs, T small_modul
 template <typename T>
 cudaError_t launch_mul_monomial(const LimbConsts<T> &lc, int limbs, const uint32_t *degrees, const T *in, T *out, uint32_t log_n, size_t batch,
                                 cudaStream_t s);
+// single-kernel multi-limb external product (lattice.cu); cudaErrorNotSupported for composed values longer than two words
+template <typename T>
+cudaError_t launch_dcrt_external_product_fused(int policy, const DevNtt<T> *tables, const RnsDev<T> &r, uint32_t log_n, uint32_t k, const T *key,
+                                               const T *in, T *out, size_t batch, bool to_coeff, cudaStream_t s);
 template <typename T> cudaError_t launch_dot_product(const Barrett<T> &br, const T *a, const T *b, T *out, size_t rows, size_t n, cudaStream_t s);
 
 }  // namespace pfhe
