@@ -393,3 +393,60 @@ def test_ternary_blind_rotation_oracle_reduces_to_rotation():
     want = O.mul_monomial(tv, (2 * n - 3 + 5 + 7) % (2 * n), q, 32).astype(np.int64)
     err = (acc[n:].astype(np.int64) - want + q // 2) % q - q // 2
     assert np.abs(err).max() <= 2 * (1 << ob.drop_bits())      # two steps, each within the gadget's rounding error
+
+
+@pytest.mark.parametrize("bits,q,log_n", [(32, Q27, 10), (32, Q27, 11), (64, Q50, 11)])
+def test_external_product_schoolbook_identity_at_baseline_shapes(bits, q, log_n):
+    """The same identity as above at the BASELINE degrees (C4: N = 2048, C5: N = 1024):
+    out_c = sum_{r,l} digit_{r,l} (*) INTT(key_{r,l,c}) in Z_q[X]/(X^N + 1), with the digits taken from the big-int model and the negacyclic
+    products computed exactly by integer convolution (np.convolve on int64 with the key split into 25-bit halves, no NTT involved)."""
+    n, beta, dt = 1 << log_n, 7, (np.uint64 if bits == 64 else np.uint32)
+    t = (O.U64NttTable if bits == 64 else O.U32NttTable)(log_n, q)
+    sb = O.ApproxSignedBasis(q, beta, None, bits); levels = sb.decompose_length()
+    g = M.Gadget(q, beta, None)
+    rng = np.random.default_rng(19)
+    key = rng.integers(0, q, (2, levels, 2, n), dtype=np.uint64).astype(dt)
+    cin = rng.integers(0, q, (2, n), dtype=np.uint64).astype(dt)
+    cin[0, :4] = (0, q - 1, q // 2, q // 2 + 1)
+    out = O.external_product_single(t, sb, 1, key.reshape(-1), cin.reshape(1, -1), to_coeff=True).reshape(2, n)
+
+    def negacyclic(d, kc):   # d: small signed int64 digits, kc: canonical words (python ints allowed) -> exact product mod q
+        lo = np.array([int(v) & ((1 << 25) - 1) for v in kc], dtype=np.int64)
+        hi = np.array([int(v) >> 25 for v in kc], dtype=np.int64)
+        full = [int(a) + (int(b) << 25) for a, b in zip(np.convolve(d, lo), np.convolve(d, hi))]   # |terms| < 64 * 2^25 * 2048 = 2^42
+        return [(full[i] - (full[i + n] if i + n < len(full) else 0)) % q for i in range(n)]
+
+    digits = np.array([[g.signed_digits(int(v)) for v in cin[r]] for r in range(2)], dtype=np.int64)   # [r][i][l]
+    for c in range(2):
+        acc = [0] * n
+        for r in range(2):
+            for l in range(levels):
+                kc = key[r, l, c].copy(); t.inverse_transform_slice(kc)
+                prod = negacyclic(digits[r, :, l], kc)
+                acc = [(x + y) % q for x, y in zip(acc, prod)]
+        assert [int(v) for v in out[c]] == acc
+
+
+def test_blind_rotation_oracle_rotates_at_the_c5_degree():
+    """Semantics of the composed (binary-secret) blind rotation at N = 1024: with noiseless trivial keys BSK_i = RGSW(s_i) (gadget rows for
+    s_i = 1, zero for s_i = 0) the accumulator ends as tv * X^(-b + sum a_i s_i) up to the gadget's rounding error per step -- i.e. the
+    CMux form defined in SURVEY App. A.6 / include/pfhe.h really evaluates the LWE phase in the exponent."""
+    q, n, n_lwe = Q27, 1024, 48
+    ot = O.U32NttTable(10, q); ob = O.ApproxSignedBasis(q, 7, None, 32); lv = ob.decompose_length()
+    rng = np.random.default_rng(23)
+    s = rng.integers(0, 2, n_lwe)
+    bsk = np.zeros((n_lwe, 2, lv, 2, n), dtype=np.uint32)
+    for i in range(n_lwe):
+        if s[i]:
+            for r in range(2):
+                for l, gl in enumerate(ob.scalars()):
+                    bsk[i, r, l, r, :] = gl % q          # NTT of the constant polynomial g_l
+    lwe = rng.integers(0, 2 * n, (1, n_lwe + 1), dtype=np.uint64).astype(np.uint32)
+    tv = rng.integers(0, q, n, dtype=np.uint64).astype(np.uint32)
+    acc = O.blind_rotate(ot, ob, bsk.reshape(-1), n_lwe, lwe, tv, batch=1)[0]
+    shift = (-int(lwe[0, n_lwe]) + int(sum(int(a) * int(b) for a, b in zip(lwe[0, :n_lwe], s)))) % (2 * n)
+    want = O.mul_monomial(tv, shift, q, 32).astype(np.int64)
+    err = (acc[n:].astype(np.int64) - want + q // 2) % q - q // 2
+    assert np.abs(err).max() <= n_lwe * (1 << ob.drop_bits())
+    erra = (acc[:n].astype(np.int64) + q // 2) % q - q // 2
+    assert np.abs(erra).max() <= n_lwe * (1 << ob.drop_bits())
