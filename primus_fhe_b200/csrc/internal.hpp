@@ -20,6 +20,9 @@ template <typename T> struct GadgetParams {
     T q, basis_m1, q_minus_basis, carry_mask, threshold, add, init_mask;
     uint32_t log_basis, levels, drop_bits;
     uint32_t has_threshold, has_init_mask;
+    // carry-free form of the same digits: digit_l = window_l(adjusted + offset) - half (balanced digits are unique), with
+    // offset = 2^(drop-1) + sum_l half 2^(drop + l*beta), half = B/2 (0 for the binary basis)
+    T offset, half;
 };
 // returns false when (q, log_basis, levels_in) is rejected by the reference constructor's asserts
 template <typename T> bool make_gadget(T q, uint32_t log_basis, uint32_t levels_in, GadgetParams<T> &g);

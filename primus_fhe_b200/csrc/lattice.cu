@@ -152,14 +152,14 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
         uint32_t terms = 0;
 #pragma unroll 1
         for (int r = 0; r < COMPS; r++) {
-            // adjusted coefficients and carries of this component stay in registers across the levels
+            // adjusted coefficient + digit offset stay in registers across the levels: the balanced digits of the reference's carry chain
+            // (init_value_carry + OnceSignedDecomposer, primitive/basis.rs:254-283, common.rs:246-259) are unique, hence equal to
+            // window_l(adjusted + offset) - half -- no carry state, three instructions per digit
             T adj[E];
-            uint32_t carries = 0;  // one carry bit per element (a register each would push the kernel into spills)
 #pragma unroll
             for (int j = 0; j < E; j++) {
-                uint32_t cj;
-                adj[j] = gadget_init<T>(g, get(r, Core::elem_index(FB0, t, j)), cj);
-                carries |= cj << j;
+                const T v = get(r, Core::elem_index(FB0, t, j));
+                adj[j] = v + ((g.has_threshold && v >= g.threshold) ? (T)(g.add + g.offset) : g.offset);
             }
 #pragma unroll 1
             for (uint32_t l = 0; l < g.levels; l++) {
@@ -167,9 +167,8 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 const uint32_t shift = g.drop_bits + l * g.log_basis;
 #pragma unroll
                 for (int j = 0; j < E; j++) {
-                    uint32_t cj = (carries >> j) & 1u;
-                    x[j] = F::load(gadget_level<T>(g, adj[j], shift, cj), cx);
-                    carries = (carries & ~(1u << j)) | (cj << j);
+                    const T win = (adj[j] >> shift) & g.basis_m1;
+                    x[j] = F::load(win >= g.half ? (T)(win - g.half) : (T)(win + (g.q - g.half)), cx);   // canonical digit mod q
                 }
                 Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);  // releases the exchange buffer for the next digit
 #pragma unroll

@@ -256,6 +256,9 @@ template <typename T> bool make_gadget(T q, uint32_t log_basis, uint32_t levels_
     g.threshold = value;
     const T all = value_bits == (uint32_t)BITS ? (T)~(T)0 : (T)(((T)1 << value_bits) - 1);
     g.add = (T)(all - (q - 1));
+    g.half = log_basis == 1 ? (T)0 : (T)(basis >> 1);
+    g.offset = drop > 0 ? (T)((T)1 << (drop - 1)) : (T)0;
+    for (uint32_t l = 0; l < levels; l++) g.offset = (T)(g.offset + (T)(g.half << (drop + l * log_basis)));
     return true;
 }
 template bool make_gadget<uint32_t>(uint32_t, uint32_t, uint32_t, GadgetParams<uint32_t> &);
