@@ -36,7 +36,7 @@ class OracleError(Exception):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
-    src = [os.path.join(_HERE, f) for f in ("pfhe_oracle.c", "oracle_impl.inc", "pfhe_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("pfhe_oracle.c", "oracle_impl.inc", "pfhe_oracle.h", "pfhe_oracle_avx512.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -336,6 +336,27 @@ class _NttTable:
 
 class U64NttTable(_NttTable):
     bits = 64
+
+    # ---- AVX-512 IFMA restatement of the reference's fast forward path (pfhe_oracle_avx512.c): the CPU baseline of bench.py ----
+    def simd_supported(self) -> bool:
+        """True when this CPU has AVX-512 IFMA and the table qualifies for the reference's BIT_SHIFT = 52 back-end (q < 2^50, N >= 16)."""
+        f = lib().o_ifma_supported; f.restype = C.c_int
+        return bool(f()) and self.q < (1 << 50) and self.n >= 16
+
+    def _simd(self):
+        if getattr(self, "_ifma", None) is None:
+            f = lib().o_ifma_create; f.restype = C.c_void_p; f.argtypes = [C.c_uint, C.c_uint64, C.c_void_p]
+            roots = np.ascontiguousarray(self.roots(), dtype=np.uint64)
+            self._ifma = f(self.log_n, self.q, _ptr(roots))
+            if not self._ifma:
+                raise OracleError(4)
+        return self._ifma
+
+    def forward_batch_simd(self, v, threads=0):
+        """forward_batch through the IFMA path (canonical outputs, bit-identical to forward_batch)."""
+        assert v.dtype == np.uint64 and v.flags.c_contiguous and self.simd_supported()
+        f = lib().o_ifma_forward_batch; f.restype = None; f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        f(self._simd(), _ptr(v), v.size // self.n, threads or max_threads())
 
 
 class U32NttTable(_NttTable):

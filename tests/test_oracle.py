@@ -450,3 +450,24 @@ def test_blind_rotation_oracle_rotates_at_the_c5_degree():
     assert np.abs(err).max() <= n_lwe * (1 << ob.drop_bits())
     erra = (acc[:n].astype(np.int64) + q // 2) % q - q // 2
     assert np.abs(erra).max() <= n_lwe * (1 << ob.drop_bits())
+
+
+def test_ifma_restatement_matches_scalar_oracle():
+    """oracle/pfhe_oracle_avx512.c (the CPU baseline of bench.py on AVX-512 IFMA hosts) is bit-identical to the scalar Harvey transform for every
+    degree it accepts, including the q-1 / 0 edge rows; skipped where the CPU lacks IFMA (the baseline then falls back to the scalar port)."""
+    t0 = O.U64NttTable(4, Q50)
+    if not t0.simd_supported():
+        pytest.skip("no AVX-512 IFMA on this host")
+    for q in (Q50, Q49, 1073692673, 132120577):
+        for log_n in (4, 5, 6, 9, 11, 12, 13):
+            if (q - 1) % (2 << log_n):
+                continue
+            t = O.U64NttTable(log_n, q)
+            rng = np.random.default_rng(log_n)
+            x = rng.integers(0, q, (5, 1 << log_n), dtype=np.uint64)
+            x[0, :] = q - 1
+            x[1, :] = 0
+            a = x.copy(); t.forward_batch(a, 1)
+            b = x.copy(); t.forward_batch_simd(b, 2)
+            assert np.array_equal(a, b), (q, log_n)
+    assert not O.U64NttTable(10, Q60).simd_supported()      # 60-bit primes are outside the BIT_SHIFT = 52 back-end
