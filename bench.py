@@ -643,6 +643,26 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
         O.U64NttTable(LOG_N, q60).forward_batch(w60, 1)
     checks["ntt_fwd_n4096_q60"] = bool(np.array_equal(u64(d60[:2]), w60))
     del d60
+    # C1: N=1024, one 32-bit prime (q = 132120577), round trip + fused product; batch 1024 is one launch of ~10 us, so the rate is
+    # also taken at batch 2^20 (4 GiB of traffic) where the kernel, not the launch, is measured
+    q32 = 132120577
+    t10 = P.U32NttTable(10, q32, device=local_rank)
+    o10 = O.U32NttTable(10, q32)
+    for nb, tag in ((1024, "batch1024"), (1 << 20, "batch1M")):
+        xa = torch.randint(0, q32, (nb, 1024), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+        xb = torch.randint(0, q32, (nb, 1024), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+        xc = torch.empty_like(xa)
+        dt = timed(lambda: t10.polymul_batch(xa, xb, xc), reps=5)
+        extra[f"c1_polymul_per_s_n1024_u32_{tag}"] = nb / dt
+        if nb > 1024:
+            extra["c1_polymul_n1024_u32_roofline"] = roof(nb * 3 * 1024 * 4 / dt)
+            dt = timed(lambda: t10.forward_batch(xc), reps=5)
+            extra["c1_ntt_fwd_n1024_u32_roofline"] = dict(roof(nb * 2 * 1024 * 4 / dt), ntt_per_s=nb / dt)
+        else:
+            want = o10.polymul_batch(xa[:4].cpu().numpy().view(np.uint32).copy(), xb[:4].cpu().numpy().view(np.uint32).copy(), 1)
+            rt = xa[:4].clone(); t10.forward_batch(rt); t10.inverse_batch(rt)
+            checks["c1_polymul_and_round_trip_n1024_u32"] = bool(np.array_equal(xc[:4].cpu().numpy().view(np.uint32), want) and torch.equal(rt, xa[:4]))
+        del xa, xb, xc
     # C4 external products: N=2048, k=1, base 2^7, batch 4096, shared key (A: u32 l=3; B: u64 l=7)
     for bits, q, tag in ((32, 132120577, "u32_l3"), (64, Q, "u64_l7")):
         tdt, ndt = (torch.int64, np.uint64) if bits == 64 else (torch.int32, np.uint32)
