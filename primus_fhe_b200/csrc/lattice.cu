@@ -146,10 +146,28 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
     static constexpr int CW = Core::CW, NV = Core::NV;
 
     // acc[c][j] (+)= sum_{r,l} fwd(digit_l(get(r, idx))) * key[r][l][c][t*E + j]
+    // kstage != nullptr: the key words of term (r, l) -- COMPS x E words per thread -- are copied asynchronously (cp.async, no registers) into a
+    // thread-private, double-buffered shared-memory slot BEFORE the digit of that term is transformed, so the L2 latency of the key hides
+    // behind the transform instead of stalling the multiply-accumulate (r01 ncu: 20 % of the stall samples were long-scoreboard waits on the
+    // key).  Layout [buffer][c][vector][thread] x 16 bytes: conflict free for the 128-bit reads.  `kthreads` = threads sharing kstage.
     template <typename GetIn, typename SyncF>
     __device__ __forceinline__ static void accumulate(GetIn get, const T *__restrict__ key, const GadgetParams<T> &g, const DevNtt<T> &tb,
-                                                      const typename F::Ctx &cx, Acc (&acc)[COMPS][E], Elem *sm, int t, SyncF sync) {
+                                                      const typename F::Ctx &cx, Acc (&acc)[COMPS][E], Elem *sm, int t, SyncF sync,
+                                                      uint4 *kstage = nullptr, int kthreads = 0, int kt = 0) {
         uint32_t terms = 0;
+        auto stage_key = [&](int r, uint32_t l, int buf) {
+            const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+#pragma unroll
+            for (int c = 0; c < COMPS; c++)
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(kstage + ((size_t)((buf * COMPS + c) * NV + v) * kthreads + kt));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(kp + (size_t)c * N + v * CW) : "memory");
+                }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int kbuf = 0;
+        if (kstage) stage_key(0, 0, 0);
 #pragma unroll 1
         for (int r = 0; r < COMPS; r++) {
             // adjusted coefficient + digit offset stay in registers across the levels: the balanced digits of the reference's carry chain
@@ -174,6 +192,15 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
                 const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+                if (kstage) {  // the next term's key starts its trip now; this term's key has had the whole transform to arrive
+                    const bool last = (r == COMPS - 1) && (l + 1 == g.levels);
+                    if (!last) {
+                        stage_key(l + 1 == g.levels ? r + 1 : r, l + 1 == g.levels ? 0u : l + 1, kbuf ^ 1);
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    } else {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    }
+                }
                 if (LA::kRenorm) {
                     if (terms == LA::kRenormEvery) {  // keep the lazy sums inside their exact range
 #pragma unroll
@@ -188,11 +215,14 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                 for (int c = 0; c < COMPS; c++) {
 #pragma unroll
                     for (int v = 0; v < NV; v++) {
-                        const typename Core::WVec kv = ldg_vec(reinterpret_cast<const typename Core::WVec *>(kp + (size_t)c * N) + v);
+                        typename Core::WVec kv;
+                        if (kstage) *reinterpret_cast<uint4 *>(&kv) = kstage[(size_t)((kbuf * COMPS + c) * NV + v) * kthreads + kt];
+                        else kv = ldg_vec(reinterpret_cast<const typename Core::WVec *>(kp + (size_t)c * N) + v);
 #pragma unroll
                         for (int w = 0; w < CW; w++) LA::mac(acc[c][v * CW + w], x[v * CW + w], kv.v[w], cx);
                     }
                 }
+                kbuf ^= 1;
             }
         }
     }
@@ -205,7 +235,7 @@ template <int LOGN, int LOGE, int PPB> constexpr int ep_min_blocks() {
     return threads >= 512 ? 1 : 512 / threads;
 }
 
-template <typename F, int LOGN, int LOGE, int COMPS, int PPB>
+template <typename F, int LOGN, int LOGE, int COMPS, int PPB, bool KPREF = false>
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ep_min_blocks<LOGN, LOGE, PPB>())
 external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, const __grid_constant__ GadgetParams<typename F::WordT> g,
                         const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ in,
@@ -234,7 +264,13 @@ external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, co
     for (int c = 0; c < COMPS; c++)
 #pragma unroll
         for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
-    EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync);
+    if constexpr (KPREF) {  // key staging area behind the exchange buffers of the CTA's groups
+        uint4 *kstage = reinterpret_cast<uint4 *>(smem_raw + sizeof(T) * PPB * N);
+        EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync, kstage, TPP * PPB,
+                       (int)threadIdx.x);
+    } else {
+        EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync);
+    }
 #pragma unroll
     for (int c = 0; c < COMPS; c++) {
         Elem x[E];
@@ -341,8 +377,21 @@ static cudaError_t run_ep_f(const DevNtt<typename F::WordT> &tb, const GadgetPar
     using T = typename F::WordT;
     constexpr int threads = (1 << (LOGN - LOGE)) * PPB;
     constexpr size_t smem = sizeof(T) * PPB * ((size_t)1 << LOGN);
-    auto k = external_product_kernel<F, LOGN, LOGE, COMPS, PPB>;
     cudaError_t e;
+    if constexpr (sizeof(T) == 8 && COMPS == 2) {  // u64 words, k = 1: optional key staging through shared memory (cp.async), see ExtProd::accumulate
+        // measured slower than the direct key loads (3.64 M against 4.87 M products/s at N = 2048, l = 7: the 64 KiB of staging halves the resident CTAs),
+        // so it is opt-in; profiles/r02_large_n_experiments.md
+        static const bool kpref = getenv("PFHE_EP_KEY_PREFETCH") && getenv("PFHE_EP_KEY_PREFETCH")[0] == '1';
+        if (kpref) {
+            constexpr size_t smem_k = smem + (size_t)2 * COMPS * ((1 << LOGE) * sizeof(T) / 16) * threads * 16;
+            auto kk = external_product_kernel<F, LOGN, LOGE, COMPS, PPB, true>;
+            if ((e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k)) != cudaSuccess) return e;
+            kk<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem_k, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
+    auto k = external_product_kernel<F, LOGN, LOGE, COMPS, PPB>;
     if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
     count_launch();
