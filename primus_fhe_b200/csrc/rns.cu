@@ -67,90 +67,169 @@ template <typename T> __device__ __forceinline__ T big_mul_add(const T *m, T v, 
     return carry;
 }
 
-// compose_to (base.rs:609-636)
-template <typename T> __device__ __forceinline__ void rns_compose(const RnsDev<T> &r, const T *residues, T *value) {
-    for (int k = 0; k < r.value_len; k++) value[k] = 0;
-    for (int i = 0; i < r.limbs; i++) {
-        const T prod = shoup<T>(residues[i], r.inv_punct[i], r.inv_punct_q[i], r.q[i]);
-        const T carry = big_mul_add<T>(r.punct[i], prod, value, r.value_len);
-        if (carry != 0 || big_ge<T>(value, r.product, r.value_len)) big_sub<T>(value, r.product, r.value_len);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(128) rns_compose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
-                                                          T *__restrict__ big, size_t count) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-        T res[kRnsMaxLimbs], value[kRnsMaxWords];
-        for (int l = 0; l < r.limbs; l++) res[l] = residues[(size_t)l * count + i];
-        rns_compose<T>(r, res, value);
-        for (int k = 0; k < r.value_len; k++) big[i * r.value_len + k] = value[k];
-    }
-}
-// decompose_big_uint_values_to: value mod q_i by Horner over the words (base.rs:457-481)
-template <typename T>
-__global__ void __launch_bounds__(128) rns_decompose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ big,
-                                                            T *__restrict__ residues, size_t count) {
+// ---- register-resident multi-word arithmetic: the limb count L is a template parameter, the composed value is held in L words
+// (value_len <= L; the unused top words of product / punct / threshold / add are zero, so uniform L-word arithmetic is exact) -----
+template <typename T, int L> struct BigRegs {
     using W = typename WideOf<T>::type;
+    static constexpr int BITS = sizeof(T) * 8;
+    // d = a - b over L words; returns the final borrow
+    __device__ __forceinline__ static T sub(const T (&a)[L], const T *b, T (&d)[L]) {
+        T borrow = 0;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            const T t = a[k] - b[k];
+            const T nb = (T)((a[k] < b[k]) | (t < borrow));
+            d[k] = t - borrow;
+            borrow = nb;
+        }
+        return borrow;
+    }
+    __device__ __forceinline__ static void add(T (&a)[L], const T *b) {
+        T carry = 0;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            const T s = a[k] + b[k], s2 = s + carry;
+            carry = (T)((s < a[k]) | (s2 < s));
+            a[k] = s2;
+        }
+    }
+    __device__ __forceinline__ static void shr_word(T (&a)[L]) {
+#pragma unroll
+        for (int k = 0; k + 1 < L; k++) a[k] = a[k + 1];
+        a[L - 1] = 0;
+    }
+    __device__ __forceinline__ static void shr_bits(T (&a)[L], uint32_t b) {  // 0 < b < BITS
+#pragma unroll
+        for (int k = 0; k + 1 < L; k++) a[k] = (T)((a[k] >> b) | (a[k + 1] << (BITS - b)));
+        a[L - 1] >>= b;
+    }
+    // compose_to (base.rs:609-636): value = sum_i (Q/q_i) * (x_i * (Q/q_i)^-1 mod q_i) mod Q, one conditional subtraction per term
+    __device__ __forceinline__ static void compose(const RnsDev<T> &r, const T (&res)[L], T (&value)[L]) {
+#pragma unroll
+        for (int k = 0; k < L; k++) value[k] = 0;
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            const T prod = shoup<T>(res[i], r.inv_punct[i], r.inv_punct_q[i], r.q[i]);
+            T carry = 0;
+#pragma unroll
+            for (int k = 0; k < L; k++) {
+                const W s = (W)r.punct[i][k] * prod + value[k] + carry;
+                value[k] = (T)s;
+                carry = (T)(s >> BITS);
+            }
+            if (i == 0) continue;  // the first term is below Q
+            T d[L];
+            const T borrow = sub(value, r.product, d);
+            const bool ge = (carry != 0) | (borrow == 0);
+#pragma unroll
+            for (int k = 0; k < L; k++) value[k] = ge ? d[k] : value[k];
+        }
+    }
+};
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256) rns_compose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
+                                                          T *__restrict__ big, size_t count) {
+    const int vl = r.value_len;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-        for (int l = 0; l < r.limbs; l++) {
-            W rem = 0;
-            for (int k = r.value_len - 1; k >= 0; k--) rem = ((rem << (sizeof(T) * 8)) | big[i * r.value_len + k]) % r.q[l];
-            residues[(size_t)l * count + i] = (T)rem;
+        T res[L], value[L];
+#pragma unroll
+        for (int l = 0; l < L; l++) res[l] = ldg_stream(residues + (size_t)l * count + i);
+        BigRegs<T, L>::compose(r, res, value);
+        T *o = big + i * (size_t)vl;
+#pragma unroll
+        for (int k = 0; k < L; k++)
+            if (k < vl) o[k] = value[k];
+    }
+}
+// decompose_big_uint_values_to (base.rs:457-481): value mod q_l = sum_k word_k * (2^(BITS k) mod q_l) mod q_l, every term a Shoup
+// product with a precomputed quotient (exact for arbitrary words)
+template <typename T, int L>
+__global__ void __launch_bounds__(256) rns_decompose_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ big,
+                                                            T *__restrict__ residues, size_t count) {
+    const int vl = r.value_len;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        T w[L];
+        const T *v = big + i * (size_t)vl;
+#pragma unroll
+        for (int k = 0; k < L; k++) w[k] = k < vl ? v[k] : (T)0;
+#pragma unroll
+        for (int l = 0; l < L; l++) {
+            const T q = r.q[l];
+            T acc = 0;
+#pragma unroll
+            for (int k = 0; k < L; k++)
+                if (k < vl) acc = mod_add<T>(acc, shoup<T>(w[k], r.pw[l][k], r.pw_q[l][k], q), q);
+            stg_stream(residues + (size_t)l * count + i, acc);
         }
     }
 }
 
 // residues[limbs][count] -> digits[levels][limbs][count]: compose, init_value_carry, unsigned digits, centred lift.
 // One thread owns VEC consecutive coefficients so that every load / store is a 16-byte vector (the kernel is bound by
-// its levels*limbs stores per coefficient).
-template <typename T>
+// its levels*limbs stores per coefficient).  The composed value lives in L registers per coefficient and is shifted down by
+// log_basis per level, so the digit window is always the low bits of word 0 (no dynamically indexed word array).
+template <typename T, int L>
 __global__ void __launch_bounds__(128) rns_gadget_kernel(const __grid_constant__ RnsDev<T> r, const T *__restrict__ residues,
                                                          T *__restrict__ digits, size_t count, size_t polys, size_t in_stride,
                                                          size_t out_stride) {
     // `polys` independent CRT polynomials: residues + p*in_stride, digits + p*out_stride
-    constexpr int BITS = sizeof(T) * 8, VEC = 16 / sizeof(T);
-    struct alignas(16) V {
+    using BR = BigRegs<T, L>;
+    constexpr int BITS = sizeof(T) * 8, VB = L <= 4 ? 16 : 8, VEC = VB / sizeof(T);  // many limbs: fewer coefficients per thread (registers)
+    using Raw = typename std::conditional<VB == 16, uint4, uint64_t>::type;
+    struct alignas(VB) V {
         T v[VEC];
     };
-    const size_t cv = count / VEC, total = polys * cv;
+    const size_t cv = count / VEC;
     const T bm1 = r.basis_m1, half = (T)((r.basis_m1 + 2) / 2);  // ceil(B/2)
-    for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = gid / cv, i = (gid % cv) * VEC;
+    const uint32_t pre = r.drop_bits ? r.drop_bits - 1 : 0;       // bits below the rounding bit
+    for (size_t p = blockIdx.y; p < polys; p += gridDim.y) {
         const T *res_in = residues + p * in_stride;
         T *dig = digits + p * out_stride;
-        T value[VEC][kRnsMaxWords + 1];
-        uint32_t carry[VEC];
-        {
-            V in[kRnsMaxLimbs];
-            for (int l = 0; l < r.limbs; l++) in[l] = *reinterpret_cast<const V *>(res_in + (size_t)l * count + i);
+        for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < cv; g += (size_t)gridDim.x * blockDim.x) {
+            const size_t i = g * VEC;
+            T value[VEC][L];
+            uint32_t carry[VEC];
+            {
+                V in[L];
 #pragma unroll
-            for (int k = 0; k < VEC; k++) {
-                T res[kRnsMaxLimbs];
-                for (int l = 0; l < r.limbs; l++) res[l] = in[l].v[k];
-                rns_compose<T>(r, res, value[k]);
-                value[k][r.value_len] = 0;
-                if (r.has_threshold && big_ge<T>(value[k], r.threshold, r.value_len)) big_add<T>(value[k], r.add, r.value_len);
-                carry[k] = r.has_init_mask ? (uint32_t)((value[k][r.init_index] & r.init_mask) != 0) : 0u;
+                for (int l = 0; l < L; l++) *reinterpret_cast<Raw *>(&in[l]) = ldg_stream(reinterpret_cast<const Raw *>(res_in + (size_t)l * count + i));
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    T res[L];
+#pragma unroll
+                    for (int l = 0; l < L; l++) res[l] = in[l].v[k];
+                    BR::compose(r, res, value[k]);
+                    if (r.has_threshold) {
+                        T d[L];
+                        if (BR::sub(value[k], r.threshold, d) == 0) BR::add(value[k], r.add);  // value >= threshold
+                    }
+                    // init_value_carry: the rounding bit (bit drop-1), then drop the low bits
+                    carry[k] = 0;
+                    if (r.drop_bits) {
+                        for (uint32_t s = 0; s < pre / BITS; s++) BR::shr_word(value[k]);
+                        if (pre % BITS) BR::shr_bits(value[k], pre % BITS);
+                        carry[k] = (uint32_t)(value[k][0] & 1);
+                        BR::shr_bits(value[k], 1);
+                    }
+                }
             }
-        }
-        for (uint32_t lv = 0; lv < r.levels; lv++) {
-            const uint32_t pos = r.drop_bits + lv * r.log_basis;
-            const int idx = pos / BITS, sh = pos % BITS;
-            T d[VEC];
+            for (uint32_t lv = 0; lv < r.levels; lv++) {
+                T d[VEC];
 #pragma unroll
-            for (int k = 0; k < VEC; k++) {
-                T lower = value[k][idx] >> sh;
-                if (sh + (int)r.log_basis > BITS && idx + 1 < r.value_len) lower |= value[k][idx + 1] << (BITS - sh);
-                const T t = (lower & bm1) + carry[k];
-                carry[k] = (t & r.carry_mask) != 0;
-                d[k] = t & bm1;
-            }
-            for (int l = 0; l < r.limbs; l++) {
-                V o;
+                for (int k = 0; k < VEC; k++) {
+                    const T t = (value[k][0] & bm1) + carry[k];
+                    carry[k] = (t & r.carry_mask) != 0;
+                    d[k] = t & bm1;
+                    BR::shr_bits(value[k], r.log_basis);
+                }
 #pragma unroll
-                for (int k = 0; k < VEC; k++) o.v[k] = (r.basis_m1 == 1 || d[k] < half) ? d[k] : r.q[l] - (bm1 + 1) + d[k];
-                *reinterpret_cast<V *>(dig + ((size_t)lv * r.limbs + l) * count + i) = o;
+                for (int l = 0; l < L; l++) {
+                    V o;
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) o.v[k] = (r.basis_m1 == 1 || d[k] < half) ? d[k] : r.q[l] - (bm1 + 1) + d[k];
+                    stg_stream(reinterpret_cast<Raw *>(dig + ((size_t)lv * L + l) * count + i), *reinterpret_cast<const Raw *>(&o));
+                }
             }
         }
     }
@@ -289,37 +368,72 @@ template <typename T> __device__ __forceinline__ T double_to_word(double v);
 template <> __device__ __forceinline__ uint32_t double_to_word<uint32_t>(double v) { return __double2uint_rz(v); }
 template <> __device__ __forceinline__ uint64_t double_to_word<uint64_t>(double v) { return __double2ull_rz(v); }
 
-template <typename T, bool EXACT>
+// NIN (input limbs) is a template parameter: the adjusted residues stay in registers.  The coefficient index is split with a shift when the
+// polynomial length is a power of two (log_n >= 0), by one 64-bit division otherwise.
+// F64 (u64 words, every modulus below 2^50 - 2^10): all modular products run on the FP64 pipe -- x*inv mod q_i and y_i * (Q/q_i mod p_k) mod p_k
+// are exact-integer-in-a-double products (6 instructions, |result| <= 0.75 p: the quotient estimate of a product below 2^100 is off by at
+// most 0.25 + the rounding to an integer), the <= 8 terms per output sum exactly (6 p < 2^53) and one fold gives the canonical residue.  The
+// integer formulation needs ~28 64-bit multiplies per coefficient of a 3 -> 2 conversion (0.31 of the HBM copy peak, integer-issue bound);
+// the FP64 one 86 FP64 instructions (HBM bound).  An input word >= 2^50 (not a canonical residue) takes the integer path for that term.
+template <typename T, int NIN, bool EXACT, bool F64>
 __global__ void __launch_bounds__(256) baseconv_kernel(const __grid_constant__ BaseConvDev<T> c, const T *__restrict__ in, T *__restrict__ out,
-                                                       size_t n, size_t polys) {
+                                                       size_t n, size_t polys, int log_n) {
     using W = typename WideOf<T>::type;
     const size_t total = polys * n;
+    const int n_out = EXACT ? 1 : c.n_out;
     for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
-        const size_t p = gid / n, j = gid % n;
-        const T *x = in + p * (size_t)c.n_in * n + j;
-        T y[kRnsMaxLimbs];
-        double agg = 0.0;
+        const size_t p = log_n >= 0 ? gid >> log_n : gid / n, j = log_n >= 0 ? gid & (n - 1) : gid % n;
+        const T *x = in + p * (size_t)NIN * n + j;
+        T xin[NIN];
 #pragma unroll
-        for (int i = 0; i < kRnsMaxLimbs; i++) {
-            if (i < c.n_in) {
-                const T xi = x[(size_t)i * n];
-                y[i] = c.inv[i] == 1 ? barrett_reduce_wide(c.in_br[i], xi, (T)0) : shoup<T>(xi, c.inv[i], c.inv_q[i], c.in_br[i].q);
+        for (int i = 0; i < NIN; i++) xin[i] = ldg_stream(x + (size_t)i * n);
+        double agg = 0.0;
+        if constexpr (F64 && sizeof(T) == 8) {
+            using F = F64LazyField;
+            double y[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) {
+                const F::Ctx cx{c.q_f[i], c.in_qinv_f[i], 0.0, 0.0, 0, 0};
+                if ((xin[i] >> 50) == 0) {
+                    const double v = F::mulmod(F::from_u64(xin[i]), c.inv_f[i], cx, 0);   // == x * inv mod q_i, |v| <= 0.75 q_i
+                    y[i] = v < 0.0 ? __dadd_rn(v, c.q_f[i]) : v;                         // canonical, as the reference's y_i
+                } else {
+                    y[i] = F::from_u64(c.inv[i] == 1 ? barrett_reduce_wide(c.in_br[i], xin[i], (T)0) : shoup<T>(xin[i], c.inv[i], c.inv_q[i], c.in_br[i].q));
+                }
+                if (EXACT) agg = __dadd_rn(agg, __ddiv_rn(y[i], c.q_f[i]));
+            }
+            for (int k = 0; k < n_out; k++) {
+                const F::Ctx cx{c.out_p_f[k], c.out_pinv_f[k], 0.0, F::kTwo52 + c.out_p_f[k], c.out_br[k].q, 0};
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NIN; i++) acc = __dadd_rn(acc, F::mulmod(y[i], c.matrix_f[k][i], cx, 0));
+                if (EXACT) {
+                    const double v = (double)double_to_word<T>(__dadd_rn(agg, 0.5));     // <= NIN
+                    acc = __dsub_rn(acc, F::mulmod(v, c.q_mod_p_f[0], cx, 0));
+                    stg_stream(out + p * n + j, (T)F::canon(acc, cx));
+                } else {
+                    stg_stream(out + (p * (size_t)c.n_out + k) * n + j, (T)F::canon(acc, cx));
+                }
+            }
+        } else {
+            T y[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) {
+                y[i] = c.inv[i] == 1 ? barrett_reduce_wide(c.in_br[i], xin[i], (T)0) : shoup<T>(xin[i], c.inv[i], c.inv_q[i], c.in_br[i].q);
                 if (EXACT) agg = __dadd_rn(agg, __ddiv_rn(word_to_double<T>(y[i]), c.q_f[i]));
             }
-        }
-        const int n_out = EXACT ? 1 : c.n_out;
-        for (int k = 0; k < n_out; k++) {
-            W acc = 0;
+            for (int k = 0; k < n_out; k++) {
+                W acc = 0;
 #pragma unroll
-            for (int i = 0; i < kRnsMaxLimbs; i++)
-                if (i < c.n_in) acc += (W)y[i] * c.matrix[k][i];
-            T r = barrett_reduce_wide(c.out_br[k], (T)acc, (T)(acc >> (sizeof(T) * 8)));
-            if (EXACT) {
-                const T v = double_to_word<T>(__dadd_rn(agg, 0.5));
-                r = mod_sub<T>(r, barrett_mul<T>(c.out_br[0], v, c.q_mod_p[0]), c.out_br[0].q);
-                out[p * n + j] = r;
-            } else {
-                out[(p * (size_t)c.n_out + k) * n + j] = r;
+                for (int i = 0; i < NIN; i++) acc += (W)y[i] * c.matrix[k][i];
+                T r = barrett_reduce_wide(c.out_br[k], (T)acc, (T)(acc >> (sizeof(T) * 8)));
+                if (EXACT) {
+                    const T v = double_to_word<T>(__dadd_rn(agg, 0.5));
+                    r = mod_sub<T>(r, barrett_mul<T>(c.out_br[0], v, c.q_mod_p[0]), c.out_br[0].q);
+                    stg_stream(out + p * n + j, r);
+                } else {
+                    stg_stream(out + (p * (size_t)c.n_out + k) * n + j, r);
+                }
             }
         }
     }
@@ -421,6 +535,13 @@ template <typename T> int make_rns(const T *moduli, size_t limbs, uint32_t log_b
         if (inv == 0 && moduli[i] != 1) return 7;
         r.inv_punct[i] = inv;
         r.inv_punct_q[i] = host::shoup_quot<T>(inv, moduli[i]);
+        // 2^(BITS k) mod q_i and its Shoup quotient (rns_decompose_kernel)
+        std::vector<T> pw{1};
+        for (int k = 0; k < value_len; k++) {
+            r.pw[i][k] = moduli[i] == 1 ? 0 : hbig_mod_word<T>(pw, moduli[i]);
+            r.pw_q[i][k] = host::shoup_quot<T>(r.pw[i][k], moduli[i]);
+            pw.insert(pw.begin(), (T)0);
+        }
     }
     if (log_basis == 0) return 0;  // RNS base only (compose / decompose)
     if ((int)log_basis >= B) return 9;
@@ -516,7 +637,14 @@ template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T
         c.in_br[i].q = in_moduli[i];
         host::barrett_ratio<T>(in_moduli[i], c.in_br[i].r0, c.in_br[i].r1);
         c.q_f[i] = (double)in_moduli[i];
+        c.in_qinv_f[i] = 1.0 / (double)in_moduli[i];
+        c.inv_f[i] = (double)c.inv[i];
     }
+    constexpr uint64_t kF64Max = ((uint64_t)1 << 50) - 1024;  // the exactness budget of the FP64 products (ntt_core.cuh, tools/f64_bounds.py)
+    bool f64 = B == 64 && !(getenv("PFHE_DISABLE_F64") && getenv("PFHE_DISABLE_F64")[0] == '1');
+    for (size_t i = 0; i < n_in; i++) f64 = f64 && (uint64_t)in_moduli[i] <= kF64Max;
+    for (size_t k = 0; k < n_out; k++) f64 = f64 && (uint64_t)out_moduli[k] <= kF64Max;
+    c.f64_ok = f64 ? 1 : 0;
     std::vector<T> prod(in.product, in.product + in.value_len);
     for (size_t k = 0; k < n_out; k++) {
         if ((out_moduli[k] >> (B - 2)) != 0) return 5;
@@ -527,19 +655,53 @@ template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T
             c.matrix[k][i] = hbig_mod_word<T>(p, out_moduli[k]);
         }
         c.q_mod_p[k] = hbig_mod_word<T>(prod, out_moduli[k]);
+        c.out_p_f[k] = (double)out_moduli[k];
+        c.out_pinv_f[k] = 1.0 / (double)out_moduli[k];
+        c.q_mod_p_f[k] = (double)c.q_mod_p[k];
+        for (size_t i = 0; i < n_in; i++) c.matrix_f[k][i] = (double)c.matrix[k][i];
     }
     return 0;
 }
 template int make_baseconv<uint32_t>(const uint32_t *, size_t, const uint32_t *, size_t, BaseConvDev<uint32_t> &);
 template int make_baseconv<uint64_t>(const uint64_t *, size_t, const uint64_t *, size_t, BaseConvDev<uint64_t> &);
 
+#define PFHE_LIMB_SWITCH(L_, CALL) \
+    switch (L_) {                  \
+        case 1: CALL(1); break;    \
+        case 2: CALL(2); break;    \
+        case 3: CALL(3); break;    \
+        case 4: CALL(4); break;    \
+        case 5: CALL(5); break;    \
+        case 6: CALL(6); break;    \
+        case 7: CALL(7); break;    \
+        case 8: CALL(8); break;    \
+        default: return cudaErrorNotSupported; \
+    }
+
+template <typename T, int NIN>
+static void run_baseconv(const BaseConvDev<T> &c, const T *in, T *out, size_t n, size_t polys, int log_n, bool exact, unsigned grid, cudaStream_t s) {
+    if constexpr (sizeof(T) == 8) {
+        if (c.f64_ok) {
+            if (exact) baseconv_kernel<T, NIN, true, true><<<grid, 256, 0, s>>>(c, in, out, n, polys, log_n);
+            else baseconv_kernel<T, NIN, false, true><<<grid, 256, 0, s>>>(c, in, out, n, polys, log_n);
+            return;
+        }
+    }
+    if (exact) baseconv_kernel<T, NIN, true, false><<<grid, 256, 0, s>>>(c, in, out, n, polys, log_n);
+    else baseconv_kernel<T, NIN, false, false><<<grid, 256, 0, s>>>(c, in, out, n, polys, log_n);
+}
 template <typename T>
 cudaError_t launch_baseconv(const BaseConvDev<T> &c, const T *in, T *out, size_t n, size_t polys, bool exact, cudaStream_t s) {
     if (!n || !polys) return cudaSuccess;
-    if (exact)
-        baseconv_kernel<T, true><<<grid_for(n * polys, 256), 256, 0, s>>>(c, in, out, n, polys);
-    else
-        baseconv_kernel<T, false><<<grid_for(n * polys, 256), 256, 0, s>>>(c, in, out, n, polys);
+    int log_n = -1;
+    if ((n & (n - 1)) == 0) {
+        log_n = 0;
+        while (((size_t)1 << log_n) < n) log_n++;
+    }
+    const unsigned grid = grid_for(n * polys, 256);
+#define PFHE_BC_CALL(NIN) run_baseconv<T, NIN>(c, in, out, n, polys, log_n, exact, grid, s)
+    PFHE_LIMB_SWITCH(c.n_in, PFHE_BC_CALL)
+#undef PFHE_BC_CALL
     count_launch();
     return cudaGetLastError();
 }
@@ -548,13 +710,17 @@ template cudaError_t launch_baseconv<uint64_t>(const BaseConvDev<uint64_t> &, co
 
 template <typename T> cudaError_t launch_rns_compose(const RnsDev<T> &r, const T *residues, T *big, size_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;
-    rns_compose_kernel<T><<<grid_for(count, 128), 128, 0, s>>>(r, residues, big, count);
+#define PFHE_RC_CALL(L) rns_compose_kernel<T, L><<<grid_for(count, 256), 256, 0, s>>>(r, residues, big, count)
+    PFHE_LIMB_SWITCH(r.limbs, PFHE_RC_CALL)
+#undef PFHE_RC_CALL
     count_launch();
     return cudaGetLastError();
 }
 template <typename T> cudaError_t launch_rns_decompose(const RnsDev<T> &r, const T *big, T *residues, size_t count, cudaStream_t s) {
     if (!count) return cudaSuccess;
-    rns_decompose_kernel<T><<<grid_for(count, 128), 128, 0, s>>>(r, big, residues, count);
+#define PFHE_RD_CALL(L) rns_decompose_kernel<T, L><<<grid_for(count, 256), 256, 0, s>>>(r, big, residues, count)
+    PFHE_LIMB_SWITCH(r.limbs, PFHE_RD_CALL)
+#undef PFHE_RD_CALL
     count_launch();
     return cudaGetLastError();
 }
@@ -565,7 +731,17 @@ cudaError_t launch_rns_gadget(const RnsDev<T> &r, const T *residues, T *digits, 
     if (count % (16 / sizeof(T)) || (in_stride % (16 / sizeof(T))) || (out_stride % (16 / sizeof(T))) || (reinterpret_cast<uintptr_t>(residues) & 15) ||
         (reinterpret_cast<uintptr_t>(digits) & 15))
         return cudaErrorNotSupported;  // polynomial lengths on this path are powers of two >= 4
-    rns_gadget_kernel<T><<<grid_for(count * polys / (16 / sizeof(T)), 128), 128, 0, s>>>(r, residues, digits, count, polys, in_stride, out_stride);
+    const size_t cv = count / ((r.limbs <= 4 ? 16 : 8) / sizeof(T));
+    unsigned gx = (unsigned)((cv + 127) / 128), gy = (unsigned)(polys < 65535 ? polys : 65535);
+    const unsigned cap = 148 * 16;  // grid-stride beyond that
+    if ((size_t)gx * gy > cap) {
+        if (gx > cap) gx = cap;
+        gy = cap / gx ? (gy < cap / gx ? gy : cap / gx) : 1;
+    }
+    const dim3 grid(gx, gy);
+#define PFHE_RG_CALL(L) rns_gadget_kernel<T, L><<<grid, 128, 0, s>>>(r, residues, digits, count, polys, in_stride, out_stride)
+    PFHE_LIMB_SWITCH(r.limbs, PFHE_RG_CALL)
+#undef PFHE_RG_CALL
     count_launch();
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@ template <typename T> struct RnsDev {
     T product[kRnsMaxWords];                 // Q = prod q_i, little endian
     T punct[kRnsMaxLimbs][kRnsMaxWords];     // Q / q_i
     T inv_punct[kRnsMaxLimbs], inv_punct_q[kRnsMaxLimbs];  // (Q/q_i)^-1 mod q_i and its Shoup quotient
+    T pw[kRnsMaxLimbs][kRnsMaxWords], pw_q[kRnsMaxLimbs][kRnsMaxWords];  // 2^(BITS k) mod q_i and its Shoup quotient (decompose)
     // gadget part (log_basis == 0: RNS base only)
     uint32_t log_basis, levels, drop_bits;
     T basis_m1, carry_mask, init_mask;
@@ -29,6 +30,10 @@ template <typename T> struct BaseConvDev {
     T matrix[kRnsMaxLimbs][kRnsMaxLimbs];          // [output k][input i]
     T q_mod_p[kRnsMaxLimbs];
     double q_f[kRnsMaxLimbs];
+    // FP64-pipe formulation (u64 words, every modulus <= 2^50 - 2^10): the same constants as exact doubles
+    int f64_ok;
+    double in_qinv_f[kRnsMaxLimbs], inv_f[kRnsMaxLimbs], out_p_f[kRnsMaxLimbs], out_pinv_f[kRnsMaxLimbs], q_mod_p_f[kRnsMaxLimbs];
+    double matrix_f[kRnsMaxLimbs][kRnsMaxLimbs];
 };
 template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T *out_moduli, size_t n_out, BaseConvDev<T> &c);
 template <typename T>
