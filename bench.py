@@ -757,15 +757,32 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
     digs = torch.empty((polys, bb2.decompose_length(), 2, 2048), dtype=torch.int64, device="cuda")
     dt = timed(lambda: bb2.gadget_decompose_batch(res_in, digs, 2048))
     stream["rns_gadget_L2_l14"] = roof(polys * 2048 * 8 * (2 + 2 * bb2.decompose_length()) / dt)
-    big = torch.empty((polys * 2048, rns.big_uint_value_len()), dtype=torch.int64, device="cuda")
-    flat = res_in.permute(1, 0, 2).contiguous().view(2, -1)
+    del res_in, digs
+    polys = 16384                                          # 32 Mi coefficients: 256 MiB per limb, beyond L2
+    cnt = polys * 2048
+    flat = torch.stack([torch.randint(0, m, (cnt,), dtype=torch.int64, device="cuda", generator=g) for m in m2], dim=0).contiguous()
+    big = torch.empty((cnt, rns.big_uint_value_len()), dtype=torch.int64, device="cuda")
     dt = timed(lambda: rns.compose_multiple_values_to(flat, big))
-    stream["rns_compose_L2"] = roof(polys * 2048 * 8 * (2 + rns.big_uint_value_len()) / dt)
-    bc = P.BaseConverter([137438822401, 137438814209, 137438773249], [Q, 1125899906629633], 64)
+    stream["rns_compose_L2"] = roof(cnt * 8 * (2 + rns.big_uint_value_len()) / dt)
+    back = torch.empty_like(flat)
+    dt = timed(lambda: rns.decompose_big_uint_values_to(big, back))
+    stream["rns_decompose_L2"] = roof(cnt * 8 * (2 + rns.big_uint_value_len()) / dt)
+    checks["rns_compose_decompose_round_trip"] = bool(torch.equal(back, flat)) and bool(np.array_equal(
+        u64(big[:4096]).reshape(-1), O.RNSBase(m2, 64).compose_multiple_values_to(u64(flat[:, :4096]).copy().reshape(-1), 4096)))
+    del flat, big, back
+    bc_in = [137438822401, 137438814209, 137438773249]
+    bc = P.BaseConverter(bc_in, [Q, 1125899906629633], 64)
     cin3 = torch.stack([torch.randint(0, m, (polys, 2048), dtype=torch.int64, device="cuda", generator=g) for m in bc.in_moduli], dim=1).contiguous()
     cout3 = torch.empty((polys, 2, 2048), dtype=torch.int64, device="cuda")
     dt = timed(lambda: bc.fast_convert_array(cin3, cout3, 2048))
-    stream["baseconv_fast_3_to_2"] = roof(polys * 2048 * 8 * 5 / dt)
+    stream["baseconv_fast_3_to_2"] = roof(cnt * 8 * 5 / dt)
+    obc = O.BaseConverter(bc_in, [Q, 1125899906629633], 64)
+    checks["baseconv_fast_3_to_2"] = bool(np.array_equal(u64(cout3[polys - 1]).reshape(-1), obc.fast_convert_array(u64(cin3[polys - 1]).copy().reshape(-1), 2048)))
+    bc1 = P.BaseConverter(bc_in, [Q], 64)
+    cex = cout3.view(-1)[:cnt]
+    dt = timed(lambda: bc1.exact_convert_array(cin3, cex, 2048))
+    stream["baseconv_exact_3_to_1"] = roof(cnt * 8 * 4 / dt)
+    del cin3, cout3
     extra["streaming_kernels"] = stream
 
 

@@ -280,9 +280,44 @@ __global__ void __launch_bounds__(256) decompose_kernel(const __grid_constant__ 
         }
     }
 }
+// 16 bytes per access (the kernel writes `levels` words per word read: it is bound by its stores), streaming hints on both sides
+template <typename T>
+__global__ void __launch_bounds__(256) decompose_vec_kernel(const __grid_constant__ GadgetParams<T> g, const T *__restrict__ values,
+                                                            T *__restrict__ digits, size_t count) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) V {
+        T v[VEC];
+    };
+    const size_t cv = count / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cv; i += (size_t)gridDim.x * blockDim.x) {
+        V in;
+        *reinterpret_cast<uint4 *>(&in) = ldg_stream(reinterpret_cast<const uint4 *>(values) + i);
+        uint32_t carry[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            if (g.has_threshold && in.v[k] >= g.threshold) in.v[k] += g.add;
+            carry[k] = g.has_init_mask ? (uint32_t)((in.v[k] & g.init_mask) != 0) : 0u;
+        }
+        for (uint32_t l = 0; l < g.levels; l++) {
+            V o;
+            const uint32_t sh = g.drop_bits + l * g.log_basis;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const T t = ((in.v[k] >> sh) & g.basis_m1) + carry[k];
+                carry[k] = (t & g.carry_mask) != 0;
+                o.v[k] = carry[k] ? (t > g.basis_m1 ? T(0) : t + g.q_minus_basis) : t;
+            }
+            stg_stream(reinterpret_cast<uint4 *>(digits + (size_t)l * count) + i, *reinterpret_cast<const uint4 *>(&o));
+        }
+    }
+}
 template <typename T> cudaError_t launch_decompose(const GadgetParams<T> &g, const T *values, T *digits, size_t count, cudaStream_t stream) {
     if (count == 0) return cudaSuccess;
-    decompose_kernel<T><<<stream_grid(count, 256), 256, 0, stream>>>(g, values, digits, count);
+    constexpr size_t VEC = 16 / sizeof(T);
+    if (count % VEC == 0 && ((reinterpret_cast<uintptr_t>(values) | reinterpret_cast<uintptr_t>(digits)) & 15) == 0)
+        decompose_vec_kernel<T><<<stream_grid(count / VEC, 256), 256, 0, stream>>>(g, values, digits, count);
+    else
+        decompose_kernel<T><<<stream_grid(count, 256), 256, 0, stream>>>(g, values, digits, count);
     count_launch();
     return cudaGetLastError();
 }

@@ -390,16 +390,19 @@ __global__ void __launch_bounds__(256) baseconv_kernel(const __grid_constant__ B
         double agg = 0.0;
         if constexpr (F64 && sizeof(T) == 8) {
             using F = F64LazyField;
+            T any = 0;
+#pragma unroll
+            for (int i = 0; i < NIN; i++) any |= xin[i];
+            if (any >> 50) {  // a word that is not a canonical residue (rare): reduce it first, (x mod q) * inv == x * inv (mod q)
+#pragma unroll
+                for (int i = 0; i < NIN; i++) xin[i] = barrett_reduce_wide(c.in_br[i], xin[i], (T)0);
+            }
             double y[NIN];
 #pragma unroll
             for (int i = 0; i < NIN; i++) {
                 const F::Ctx cx{c.q_f[i], c.in_qinv_f[i], 0.0, 0.0, 0, 0};
-                if ((xin[i] >> 50) == 0) {
-                    const double v = F::mulmod(F::from_u64(xin[i]), c.inv_f[i], cx, 0);   // == x * inv mod q_i, |v| <= 0.75 q_i
-                    y[i] = v < 0.0 ? __dadd_rn(v, c.q_f[i]) : v;                         // canonical, as the reference's y_i
-                } else {
-                    y[i] = F::from_u64(c.inv[i] == 1 ? barrett_reduce_wide(c.in_br[i], xin[i], (T)0) : shoup<T>(xin[i], c.inv[i], c.inv_q[i], c.in_br[i].q));
-                }
+                const double v = F::mulmod(F::from_u64(xin[i]), c.inv_f[i], cx, 0);   // == x * inv mod q_i, |v| <= 0.75 q_i
+                y[i] = v < 0.0 ? __dadd_rn(v, c.q_f[i]) : v;                         // canonical, as the reference's y_i
                 if (EXACT) agg = __dadd_rn(agg, __ddiv_rn(y[i], c.q_f[i]));
             }
             for (int k = 0; k < n_out; k++) {

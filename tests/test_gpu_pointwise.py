@@ -107,13 +107,13 @@ def test_decompose_matches_oracle(bits, q, log_basis, rev):
     gb = P.ApproxSignedBasis(q, log_basis, rev, bits)
     assert gb.decompose_length() == ob.decompose_length() and gb.drop_bits() == ob.drop_bits()
     rng = np.random.default_rng(11)
-    n = 10007
-    v = rng.integers(0, q, n, dtype=np.uint64).astype(dt)
-    v[:4] = [0, q - 1, q // 2, min(q - 1, (ob.threshold() or 1))]
-    want = ob.decompose_slice(v)
-    dig = torch.empty((gb.decompose_length(), n), dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
-    gb.decompose_batch(_dev(v), dig)
-    assert np.array_equal(_host(dig, dt), want)
+    for n in (10007, 10008):   # scalar kernel (ragged length) / 16-byte vector kernel
+        v = rng.integers(0, q, n, dtype=np.uint64).astype(dt)
+        v[:4] = [0, q - 1, q // 2, min(q - 1, (ob.threshold() or 1))]
+        want = ob.decompose_slice(v)
+        dig = torch.empty((gb.decompose_length(), n), dtype=torch.int64 if bits == 64 else torch.int32, device="cuda")
+        gb.decompose_batch(_dev(v), dig)
+        assert np.array_equal(_host(dig, dt), want)
 
 
 def test_rns_lift_and_extract_lwe():

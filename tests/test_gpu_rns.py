@@ -5,7 +5,7 @@ primus_rns/tests/rns.rs:65-343 and the big-int model).  Everything here is bit-e
 import numpy as np
 import pytest
 
-from conftest import Q27, Q49, Q50, Q50B
+from conftest import Q27, Q49, Q50, Q50B, Q60
 
 pytestmark = pytest.mark.gpu
 
@@ -54,7 +54,8 @@ def _rand_res(rng, moduli, n, dt):
     return r
 
 
-CASES = [(32, [P27A, P27B]), (64, [Q50, Q50B]), (64, [Q50, Q50B, Q49]), (64, [Q50]), (32, [Q27]), (64, "c3")]
+CASES = [(32, [P27A, P27B]), (64, [Q50, Q50B]), (64, [Q50, Q50B, Q49]), (64, [Q50]), (32, [Q27]), (64, "c3"),
+         (64, [17, 19, 23]), (32, [3, 5, 7, 11, 13]), (64, [Q60, Q50, Q49, Q50B])]   # value_len < limbs; a 60-bit limb
 
 
 @pytest.mark.parametrize("bits,moduli", CASES)
@@ -78,7 +79,7 @@ def test_rns_constructor_compose_decompose(bits, moduli):
     g.decompose_big_uint_values_to(big, back)
     assert np.array_equal(_host(back, dt).reshape(res.shape), res)
     # values >= Q are legal decompose inputs (base.rs:457-481 reduces word by word)
-    junk = rng.integers(0, 1 << 62, n * g.big_uint_value_len(), dtype=np.uint64).astype(dt)
+    junk = rng.integers(0, 1 << 64, n * g.big_uint_value_len(), dtype=np.uint64).astype(dt)
     g.decompose_big_uint_values_to(_dev(junk), back)
     assert np.array_equal(_host(back, dt).reshape(-1), o.decompose_big_uint_values_to(junk, n))
 
@@ -250,6 +251,22 @@ def test_base_converter_matches_oracle(bits, in_m, out_m):
     if len(out_m) > 1:
         with pytest.raises(P.PfheError):
             gc.exact_convert_array(_dev(cin), out1, n)
+    # words that are not canonical residues (any word value: the reference reduces them with the Shoup / Barrett product), the extreme
+    # residues 0 and q_i - 1, and a polynomial length that is not a power of two (index split by division)
+    n2 = 100
+    wild = rng.integers(0, 1 << bits, (polys, len(in_m), n2), dtype=np.uint64).astype(dt)
+    wild[0, :, :4] = 0
+    for i, m in enumerate(in_m):
+        wild[0, i, 4:8] = m - 1
+    wild[1] = np.stack([rng.integers(0, m, n2, dtype=np.uint64).astype(dt) for m in in_m])
+    want = np.stack([oc.fast_convert_array(wild[p].reshape(-1), n2).reshape(len(out_m), n2) for p in range(polys)])
+    out = torch.empty(polys * len(out_m) * n2, dtype=tdt, device="cuda")
+    gc.fast_convert_array(_dev(wild), out, n2)
+    assert np.array_equal(_host(out, dt).reshape(want.shape), want)
+    want1 = np.stack([o1.exact_convert_array(wild[p].reshape(-1), n2) for p in range(polys)])
+    out1 = torch.empty(polys * n2, dtype=tdt, device="cuda")
+    g1.exact_convert_array(_dev(wild), out1, n2)
+    assert np.array_equal(_host(out1, dt).reshape(want1.shape), want1)
 
 
 def test_base_converter_reference_case():
