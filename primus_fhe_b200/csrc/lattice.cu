@@ -153,7 +153,7 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
     template <typename GetIn, typename SyncF>
     __device__ __forceinline__ static void accumulate(GetIn get, const T *__restrict__ key, const GadgetParams<T> &g, const DevNtt<T> &tb,
                                                       const typename F::Ctx &cx, Acc (&acc)[COMPS][E], Elem *sm, int t, SyncF sync,
-                                                      uint4 *kstage = nullptr, int kthreads = 0, int kt = 0) {
+                                                      uint4 *kstage = nullptr, int kthreads = 0, int kt = 0, bool l1_prefetch = false) {
         uint32_t terms = 0;
         auto stage_key = [&](int r, uint32_t l, int buf) {
             const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
@@ -188,10 +188,14 @@ template <typename F, int LOGN, int LOGE, int COMPS> struct ExtProd {
                     const T win = (adj[j] >> shift) & g.basis_m1;
                     x[j] = F::load(win >= g.half ? (T)(win - g.half) : (T)(win + (g.q - g.half)), cx);   // canonical digit mod q
                 }
+                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
+                if (l1_prefetch) {  // pull this term's key lines from L2 into L1 while the digit is transformed (no registers held)
+#pragma unroll
+                    for (int c = 0; c < COMPS; c++) asm volatile("prefetch.global.L1 [%0];" ::"l"(kp + (size_t)c * N));
+                }
                 Core::template fwd_from<0, true>(x, sm, tb, cx, t, sync);  // releases the exchange buffer for the next digit
 #pragma unroll
                 for (int j = 0; j < E; j++) x[j] = LA::prepare(x[j], cx);
-                const T *kp = key + ((size_t)(r * g.levels + l) * COMPS) * N + (size_t)t * E;
                 if (kstage) {  // the next term's key starts its trip now; this term's key has had the whole transform to arrive
                     const bool last = (r == COMPS - 1) && (l + 1 == g.levels);
                     if (!last) {
@@ -235,7 +239,7 @@ template <int LOGN, int LOGE, int PPB> constexpr int ep_min_blocks() {
     return threads >= 512 ? 1 : 512 / threads;
 }
 
-template <typename F, int LOGN, int LOGE, int COMPS, int PPB, bool KPREF = false>
+template <typename F, int LOGN, int LOGE, int COMPS, int PPB, int KPREF = 0>  // key path: 0 direct loads, 1 cp.async staging, 2 L1 prefetch
 __global__ void __launch_bounds__((1 << (LOGN - LOGE)) * PPB, ep_min_blocks<LOGN, LOGE, PPB>())
 external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, const __grid_constant__ GadgetParams<typename F::WordT> g,
                         const typename F::WordT *__restrict__ key, const typename F::WordT *__restrict__ in,
@@ -264,7 +268,9 @@ external_product_kernel(const __grid_constant__ DevNtt<typename F::WordT> tb, co
     for (int c = 0; c < COMPS; c++)
 #pragma unroll
         for (int j = 0; j < E; j++) LA::zero(acc[c][j]);
-    if constexpr (KPREF) {  // key staging area behind the exchange buffers of the CTA's groups
+    if constexpr (KPREF == 2) {
+        EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync, nullptr, 0, 0, true);
+    } else if constexpr (KPREF == 1) {  // key staging area behind the exchange buffers of the CTA's groups
         uint4 *kstage = reinterpret_cast<uint4 *>(smem_raw + sizeof(T) * PPB * N);
         EP::accumulate([&](int r, int idx) { return __ldg(cin + (size_t)r * N + idx); }, key, g, tb, cx, acc, sm, t, sync, kstage, TPP * PPB,
                        (int)threadIdx.x);
@@ -381,10 +387,17 @@ static cudaError_t run_ep_f(const DevNtt<typename F::WordT> &tb, const GadgetPar
     if constexpr (sizeof(T) == 8 && COMPS == 2) {  // u64 words, k = 1: optional key staging through shared memory (cp.async), see ExtProd::accumulate
         // measured slower than the direct key loads (3.64 M against 4.87 M products/s at N = 2048, l = 7: the 64 KiB of staging halves the resident CTAs),
         // so it is opt-in; profiles/r02_large_n_experiments.md
-        static const bool kpref = getenv("PFHE_EP_KEY_PREFETCH") && getenv("PFHE_EP_KEY_PREFETCH")[0] == '1';
-        if (kpref) {
+        static const int kpref = getenv("PFHE_EP_KEY_PREFETCH") ? atoi(getenv("PFHE_EP_KEY_PREFETCH")) : 0;
+        if (kpref == 2) {
+            auto kk = external_product_kernel<F, LOGN, LOGE, COMPS, PPB, 2>;
+            if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            kk<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
+            count_launch();
+            return cudaGetLastError();
+        }
+        if (kpref == 1) {
             constexpr size_t smem_k = smem + (size_t)2 * COMPS * ((1 << LOGE) * sizeof(T) / 16) * threads * 16;
-            auto kk = external_product_kernel<F, LOGN, LOGE, COMPS, PPB, true>;
+            auto kk = external_product_kernel<F, LOGN, LOGE, COMPS, PPB, 1>;
             if ((e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k)) != cudaSuccess) return e;
             kk<<<(unsigned)((batch + PPB - 1) / PPB), threads, smem_k, stream>>>(tb, g, key, in, out, batch, to_coeff ? 1 : 0);
             count_launch();
