@@ -62,7 +62,9 @@ for lb, lvl in ((7, None), (4, 5)):
     for tc in (True, False):
         o = torch.empty_like(cin); t.external_product_batch(1, lb, lvl, key_, cin, o, tc); out[f"ep32_n2048_b{lb}_{int(tc)}"] = dig(o)
 # multi-limb external product: single fused kernel vs gadget kernel + per-limb kernel (PFHE_DCRT_EP_TWO_KERNEL=1)
-for bits, m2, lb, lvl in ((64, [1125899906826241, 1125899906629633], 7, None), (32, [134215681, 134176769], 7, None), (64, [1125899906826241, 1152921504606830593], 9, 5)):
+for bits, m2, lb, lvl in ((64, [1125899906826241, 1125899906629633], 7, None), (32, [134215681, 134176769], 7, None), (64, [1125899906826241, 1152921504606830593], 9, 5),
+                          (64, [1125899906826241, 1125899906629633, 562949953392641], 7, None), (32, [134215681, 134176769, 132120577, 268369921], 7, 11),
+                          (64, [1125899906826241, 1125899906629633, 562949953392641, 1152921504606830593], 11, None)):
     tdt = torch.int64 if bits == 64 else torch.int32
     dcx = (P.U64DcrtTable if bits == 64 else P.U32DcrtTable)(10, m2)
     bbx = P.BigUintApproxSignedBasis(P.RNSBase(m2, bits), lb, lvl)
@@ -70,7 +72,7 @@ for bits, m2, lb, lvl in ((64, [1125899906826241, 1125899906629633], 7, None), (
     keyx = torch.stack([torch.from_numpy(rng.integers(0, m, (2 * lvx * 2, 1024), dtype=np.uint64).astype(np.int64)).to(tdt) for m in m2], dim=1).contiguous().cuda()
     cinx = torch.stack([torch.from_numpy(rng.integers(0, m, (3 * 2, 1024), dtype=np.uint64).astype(np.int64)).to(tdt) for m in m2], dim=1).contiguous().cuda()
     for tc in (True, False):
-        ox = torch.empty_like(cinx); P.dcrt_external_product_batch(dcx, bbx, 1, keyx, cinx, ox, tc); out[f"dcrt_ep{bits}_{lb}_{int(tc)}"] = dig(ox)
+        ox = torch.empty_like(cinx); P.dcrt_external_product_batch(dcx, bbx, 1, keyx, cinx, ox, tc); out[f"dcrt_ep{bits}_L{len(m2)}_{lb}_{int(tc)}"] = dig(ox)
 # blind rotation: re-scheduled u32 kernel (lattice32.cu) vs the generic lattice kernel (PFHE_BR_FAST=0)
 t = P.U32NttTable(10, 132120577)
 for lb, lvl, nl in ((7, None, 24), (4, 5, 8), (1, 6, 8)):
@@ -95,7 +97,8 @@ def test_all_kernel_variants_agree_bit_for_bit():
     base = _run({})
     for env in ({"PFHE_NTT_TMA": "0"}, {"PFHE_F64_LAZY": "0"}, {"PFHE_DISABLE_F64": "1"}, {"PFHE_DISABLE_WIDE32": "1"},
                 {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}, {"PFHE_BR_FAST": "0"}, {"PFHE_BR_MINB": "5"}, {"PFHE_EP_FAST": "0"},
-                {"PFHE_POLYMUL_STASH": "0"}, {"PFHE_STAGE": "0"}, {"PFHE_DCRT_EP_TWO_KERNEL": "1"}, {"PFHE_EP_KEY_PREFETCH": "1"}):
+                {"PFHE_POLYMUL_STASH": "0"}, {"PFHE_STAGE": "0"}, {"PFHE_DCRT_EP_TWO_KERNEL": "1"}, {"PFHE_EP_KEY_PREFETCH": "1"}, {"PFHE_EP_KEY_PREFETCH": "2"},
+                {"PFHE_DCRT_EP_FUSED_WIDE": "1"}):
         other = _run(env)
         diff = [k for k in base if base[k] != other[k]]
         assert not diff, (env, diff)

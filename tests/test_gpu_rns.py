@@ -150,7 +150,11 @@ def test_gadget_digits_match_oracle(bits, moduli, beta, rev):
 @pytest.mark.parametrize("bits,moduli,log_n,beta,rev,k", [(64, [Q50, Q50B], 10, 9, 4, 1), (64, [Q50, Q50B, Q49], 10, 12, 3, 2),
                                                           (32, [P27A, P27B], 10, 7, None, 1), (64, [Q50, Q50B], 11, 7, None, 1),
                                                           (64, [Q50], 10, 7, None, 1), (64, "c3", 10, 25, None, 1),
-                                                          (64, [Q50, Q50B], 4, 9, 4, 1)])
+                                                          (64, [Q50, Q50B], 4, 9, 4, 1),
+                                                          # composed values of three / four words in the single fused kernel (k = 1)
+                                                          (64, [Q50, Q50B, Q49], 10, 7, None, 1), (64, [Q50, Q50B, Q49], 11, 13, 3, 1),
+                                                          (64, [Q50, Q50B, Q49, Q60], 10, 11, None, 1), (64, [Q50, Q50B, Q49, 1125899904679937], 10, 16, None, 1),
+                                                          (32, [P27A, P27B, Q27], 10, 7, None, 1), (32, [P27A, P27B, Q27, 268369921], 10, 7, 11, 1)])
 @pytest.mark.parametrize("to_coeff", [True, False])
 def test_dcrt_external_product_matches_oracle(bits, moduli, log_n, beta, rev, k, to_coeff):
     """CrtGlwe::mul_dcrt_ggsw_to for L >= 1 limbs (primus_lattice/src/glwe/crt.rs:200-227); parity unpinned by any
