@@ -418,6 +418,20 @@ def main():
     for _ in range(2):
         table.transform_slices(pageable)
     e2e_pageable = world * pg_batch * 2 / max_over_ranks(time.perf_counter() - t0)
+    # the caller's own buffer page-locked in place once (pfhe_host_register; ffi/primus_cuda `Pinned`): registration cost reported, not timed
+    t0 = time.perf_counter()
+    reg = P.registered_host_buffer(pageable)
+    reg.__enter__()
+    reg_seconds = time.perf_counter() - t0
+    try:
+        table.transform_slices(pageable)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            table.transform_slices(pageable)
+        e2e_registered = world * pg_batch * 2 / max_over_ranks(time.perf_counter() - t0)
+    finally:
+        reg.__exit__(None, None, None)
     del host, pageable
 
     # ---- bootstraps/s: BASELINE config 5, every rank runs its share of the 10,000 ciphertexts ---------------------------------
@@ -486,6 +500,8 @@ def main():
                     "api": "pfhe_ntt64_transform_slices (host-slice shim of NttTable::transform_slice, pinned host memory)",
                     "pageable": {"value": e2e_pageable, "unit": UNIT, "batch": pg_batch,
                                  "note": "same call on pageable memory (numpy buffer): what a Rust `&mut [u64]` caller passes"},
+                    "registered": {"value": e2e_registered, "unit": UNIT, "batch": pg_batch, "register_seconds": reg_seconds,
+                                   "note": "the same numpy buffer page-locked in place once with pfhe_host_register (not inside the timed region)"},
                     "pcie_gbs_per_direction_per_gpu": e2e_bytes_per_s / 2 / 1e9,
                     "pcie_frac": (e2e_bytes_per_s / 2 / 1e9) / pcie["per_direction_gbs"][str(world)] if pcie and str(world) in pcie.get("per_direction_gbs", {}) else None,
                     "pcie_note": "host<->device bytes (4 GiB per step per GPU) bound this number: see profiles/r02_pcie_concurrent.json for the "

@@ -457,6 +457,20 @@ pfhe_status pfhe_lwe64_modulus_switch_batch(uint64_t q, uint32_t log_2n, const u
 pfhe_status pfhe_lwe32_modulus_switch_batch(uint32_t q, uint32_t log_2n, const uint32_t *lwe, uint32_t *out, size_t count, void *stream);
 
 /* ===================================================================================== */
+/* Host buffers of the *_slices entry points                                               */
+/* ===================================================================================== */
+/* The *_slices shims take plain host pointers -- the `&mut [T]` of NttTable::transform_slice (primus_data/src/traits.rs:20) lives in
+ * pageable memory -- and stage pageable data through pinned bounce buffers (about half the PCIe rate: one extra pass over host DRAM per
+ * direction).  A caller that reuses a long-lived buffer can page-lock it IN PLACE once; the shims recognise registered memory
+ * (cudaPointerGetAttributes) and then copy straight from / to it at the full PCIe rate.  The registration is portable across devices
+ * (the multi-device drivers use it too).  The caller must unregister before freeing or reallocating the buffer.
+ * PFHE_ERR_INVALID_ARG: null pointer / zero length; PFHE_ERR_CUDA: the range cannot be locked (already registered, limits). */
+pfhe_status pfhe_host_register(void *host_ptr, size_t bytes);
+pfhe_status pfhe_host_unregister(void *host_ptr);
+/* 1 if the shims would stage `host_ptr` through bounce buffers (pageable memory), 0 if it is page-locked / registered */
+int pfhe_host_is_pageable(const void *host_ptr);
+
+/* ===================================================================================== */
 /* Multi-device drivers (round 2): one process, several GPUs, no torch                     */
 /* ===================================================================================== */
 /* NttTable is Send + Sync (primus_ntt/src/ntt/mod.rs:16): the reference lets a caller fan a batch out over threads.  Here the

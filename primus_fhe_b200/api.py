@@ -718,6 +718,34 @@ def modulus_switch_batch(q, log_2n, lwe, out, bits=64):
     check(f(int(q), int(log_2n), _dev_ptr(lwe, bits), _dev_ptr(out, 32, lwe.numel()), lwe.numel(), _stream()))
 
 
+class registered_host_buffer:
+    """Context manager: page-lock a caller-owned numpy buffer in place (pfhe_host_register) so that the *_slices shims copy straight
+    from / to it instead of staging through bounce buffers; unregisters on exit.  Mirrors the RAII guard of the Rust FFI crate."""
+
+    def __init__(self, array):
+        self.array = array
+        self._ptr = array.ctypes.data
+
+    def __enter__(self):
+        f = lib().pfhe_host_register
+        f.argtypes = [C.c_void_p, C.c_size_t]
+        check(f(self._ptr, self.array.nbytes))
+        return self.array
+
+    def __exit__(self, *exc):
+        f = lib().pfhe_host_unregister
+        f.argtypes = [C.c_void_p]
+        check(f(self._ptr))
+        return False
+
+
+def host_is_pageable(array) -> bool:
+    f = lib().pfhe_host_is_pageable
+    f.argtypes = [C.c_void_p]
+    f.restype = C.c_int
+    return bool(f(array.ctypes.data))
+
+
 class MultiNttTable:
     """The same (log_n, q) table replicated on several devices of one process; host-slice calls are split into contiguous
     shards, one host thread per device (pfhe_multi_*).  `devices` may repeat a device index."""

@@ -472,4 +472,19 @@ pfhe_status pfhe_uintntt16_inverse_transform_slices(const pfhe_uintntt16 *t, uin
     return t ? uint16_transform(t->inner, polys, batch, false) : PFHE_ERR_INVALID_ARG;
 }
 
+// ---- page-locking of caller-owned host buffers --------------------------------------------------------------------------------------
+pfhe_status pfhe_host_register(void *host_ptr, size_t bytes) {
+    if (!host_ptr || !bytes) return PFHE_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return PFHE_OK;
+}
+pfhe_status pfhe_host_unregister(void *host_ptr) {
+    if (!host_ptr) return PFHE_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return PFHE_OK;
+}
+int pfhe_host_is_pageable(const void *host_ptr) { return host_is_pageable(host_ptr) ? 1 : 0; }
+
 }  // extern "C"

@@ -197,3 +197,26 @@ def test_ternary_blind_rotation_matches_oracle(log_basis, levels, n_lwe, batch):
         t11 = P.U32NttTable(11, q)
         t11.blind_rotate_ternary_batch(log_basis, levels, d(bp), d(bm), 1, d(lwe[:1, :2].copy()), d(np.zeros(2048, np.uint32)),
                                        torch.empty((1, 4096), dtype=torch.int32, device="cuda"))
+
+
+def test_registered_host_buffer_takes_the_direct_path():
+    """pfhe_host_register: a caller-owned pageable buffer page-locked in place is no longer staged; results are identical."""
+    import primus_fhe_b200 as P
+    from oracle import oracle as O
+    q, log_n, batch = 1125899906826241, 12, 600      # 19 MiB: above the staging threshold
+    rng = np.random.default_rng(21)
+    a = rng.integers(0, q, (batch, 1 << log_n), dtype=np.uint64)
+    want = a[:4].copy()
+    O.U64NttTable(log_n, q).forward_batch(want)
+    t = P.U64NttTable(log_n, q)
+    staged = a.copy()
+    assert P.host_is_pageable(staged)
+    t.transform_slices(staged)
+    direct = a.copy()
+    with P.registered_host_buffer(direct):
+        assert not P.host_is_pageable(direct)
+        t.transform_slices(direct)
+    assert P.host_is_pageable(direct)
+    assert np.array_equal(staged, direct) and np.array_equal(direct[:4], want)
+    with pytest.raises(P.PfheError):
+        P.registered_host_buffer(np.empty(0, dtype=np.uint64)).__enter__()
