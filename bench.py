@@ -646,6 +646,15 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
     for _ in range(4):
         O.U64NttTable(13, Q).forward_batch(w13, 1)
     checks["ntt_fwd_n8192"] = bool(np.array_equal(u64(d13[:2]), w13))
+    # N = 8192 fused product (C2 names the product at both sizes); inputs reduced mod q first (d13 holds transform outputs: already canonical)
+    q13 = batch // 4
+    a13, b13, c13 = d13[:q13], d13[q13:2 * q13], torch.empty_like(d13[:q13])
+    dt = timed(lambda: t13.polymul_batch(a13, b13, c13))
+    extra["polymul_per_s_n8192_u64"] = q13 / dt
+    fp13 = 3 * (4096 * 13 * 8 + 2 * 8192 * 3 + 8192 * 4) + 8192 * 12
+    extra["polymul_n8192_u64_roofline"] = dict(roof(q13 * 3 * 8192 * 8 / dt), fp64_instr_per_product=fp13, frac_of_fp64_pipe=q13 / dt * fp13 / FP64_PEAK)
+    checks["polymul_n8192"] = bool(np.array_equal(u64(c13[:2]), O.U64NttTable(13, Q).polymul_batch(u64(a13[:2]).copy(), u64(b13[:2]).copy(), 1)))
+    del c13
     # 60-bit prime (integer pipe)
     q60 = 1152921504606830593
     t60 = P.U64NttTable(LOG_N, q60, device=local_rank)
@@ -671,9 +680,12 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
         dt = timed(lambda: t10.polymul_batch(xa, xb, xc), reps=5)
         extra[f"c1_polymul_per_s_n1024_u32_{tag}"] = nb / dt
         if nb > 1024:
-            extra["c1_polymul_n1024_u32_roofline"] = roof(nb * 3 * 1024 * 4 / dt)
+            pk32 = modmul_peak(P, local_rank)   # bare u32 Shoup products per second, measured live
+            mm_poly = 3 * 512 * 10 + 1024       # three transforms of (N/2) log2 N butterflies + the pointwise products
+            extra["c1_polymul_n1024_u32_roofline"] = dict(roof(nb * 3 * 1024 * 4 / dt), modmuls_per_product=mm_poly, modmul_peak=pk32,
+                                                          frac_of_modmul_roof=nb / dt * mm_poly / pk32, bound="integer pipe (binding) / hbm")
             dt = timed(lambda: t10.forward_batch(xc), reps=5)
-            extra["c1_ntt_fwd_n1024_u32_roofline"] = dict(roof(nb * 2 * 1024 * 4 / dt), ntt_per_s=nb / dt)
+            extra["c1_ntt_fwd_n1024_u32_roofline"] = dict(roof(nb * 2 * 1024 * 4 / dt), ntt_per_s=nb / dt, frac_of_modmul_roof=nb / dt * 5120 / pk32)
         else:
             want = o10.polymul_batch(xa[:4].cpu().numpy().view(np.uint32).copy(), xb[:4].cpu().numpy().view(np.uint32).copy(), 1)
             rt = xa[:4].clone(); t10.forward_batch(rt); t10.inverse_batch(rt)

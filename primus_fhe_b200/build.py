@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpfhe_cuda.so")
-SOURCES = ["ntt.cu", "pointwise.cu", "lattice.cu", "lattice_dcrt.cu", "lattice32.cu", "lattice32_ep.cu", "rns.cu", "capi.cu", "capi_ext.cu"]
+SOURCES = ["ntt.cu", "ntt_cluster.cu", "pointwise.cu", "lattice.cu", "lattice_dcrt.cu", "lattice32.cu", "lattice32_ep.cu", "rns.cu", "capi.cu", "capi_ext.cu"]
 HEADERS = ["modarith.cuh", "ntt_core.cuh", "internal.hpp", "host_math.hpp", "rns.hpp", "tma.cuh", "handles.hpp", "lattice32.cuh", "lattice_core.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

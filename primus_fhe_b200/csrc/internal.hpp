@@ -50,6 +50,9 @@ template <typename T> struct LimbConsts {
     Barrett<T> br[kMaxLimbs];
     T scalar[kMaxLimbs], scalar_q[kMaxLimbs];
 };
+// N = 16384 u64 FP64 transforms on a 2-CTA cluster (ntt_cluster.cu); mode 0 forward, 1 inverse, 2 fused product out = a * b
+cudaError_t launch_ntt_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, int mode, const uint64_t *a,
+                               const uint64_t *b, uint64_t *out, size_t npolys, cudaStream_t s);
 template <typename T>
 cudaError_t launch_slice_op(int op, const LimbConsts<T> &lc, int limbs, const T *a, const T *b, const T *c, T *out,
                             size_t rows, size_t n, cudaStream_t stream, size_t b_group = 1);

@@ -307,6 +307,31 @@ __global__ void __launch_bounds__(256) rns_lift_scaled_acc_kernel(const __grid_c
         }
     }
 }
+// 16 bytes per access (count a multiple of the vector length, 16-byte aligned pointers)
+template <typename T>
+__global__ void __launch_bounds__(256) rns_lift_scaled_acc_vec_kernel(const __grid_constant__ LiftScaleConsts<T> lc, const T *__restrict__ small,
+                                                                      T *__restrict__ acc, size_t count) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) V {
+        T v[VEC];
+    };
+    const size_t cv = count / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cv; i += (size_t)gridDim.x * blockDim.x) {
+        V in;
+        *reinterpret_cast<uint4 *>(&in) = ldg_stream(reinterpret_cast<const uint4 *>(small) + i);
+        for (int l = 0; l < lc.limbs; l++) {
+            uint4 *p = reinterpret_cast<uint4 *>(acc + (size_t)l * count) + i;
+            V a;
+            *reinterpret_cast<uint4 *>(&a) = ldg_stream(p);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const T centred = (lc.unsigned_mode || in.v[k] < lc.half) ? in.v[k] : lc.temp[l] + in.v[k];
+                a.v[k] = mod_add<T>(a.v[k], shoup_exact<T>(centred, lc.f[l], lc.fq[l], lc.q[l]), lc.q[l]);
+            }
+            stg_stream(p, *reinterpret_cast<const uint4 *>(&a));
+        }
+    }
+}
 
 // p * X^r in Z_q[X]/(X^N+1), r in [0, 2N): rotate right by r mod N, negate the wrapped part, flip all when r >= N.
 // polys are [batch][limbs][N]; degrees[batch]
@@ -777,7 +802,11 @@ cudaError_t launch_rns_lift_scaled_acc(const T *moduli, int limbs, T small_modul
         lc.f[l] = scalars[l];
         lc.fq[l] = host::shoup_quot<T>(scalars[l], moduli[l]);
     }
-    rns_lift_scaled_acc_kernel<T><<<grid_for(count, 256), 256, 0, s>>>(lc, small, acc, count);
+    constexpr size_t VEC = 16 / sizeof(T);
+    if (count % VEC == 0 && ((reinterpret_cast<uintptr_t>(small) | reinterpret_cast<uintptr_t>(acc)) & 15) == 0)
+        rns_lift_scaled_acc_vec_kernel<T><<<grid_for(count / VEC, 256), 256, 0, s>>>(lc, small, acc, count);
+    else
+        rns_lift_scaled_acc_kernel<T><<<grid_for(count, 256), 256, 0, s>>>(lc, small, acc, count);
     count_launch();
     return cudaGetLastError();
 }

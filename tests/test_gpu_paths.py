@@ -23,7 +23,8 @@ out = {}
 def dig(t): return hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()
 rng = np.random.default_rng(123)
 for bits, log_n, q, batch in [(64, 12, 1125899906826241, 5), (64, 11, 1125899906826241, 7), (64, 13, 1125899906826241, 3),
-                              (64, 10, 1125899906826241, 9), (32, 10, 132120577, 9), (32, 12, 268369921, 3), (32, 13, 132120577, 2)]:
+                              (64, 10, 1125899906826241, 9), (32, 10, 132120577, 9), (32, 12, 268369921, 3), (32, 13, 132120577, 2),
+                              (64, 14, 1125899904679937, 3)]:
     n = 1 << log_n
     t = (P.U64NttTable if bits == 64 else P.U32NttTable)(log_n, q)
     x = rng.integers(0, q, (batch, n), dtype=np.uint64)
@@ -36,6 +37,11 @@ for bits, log_n, q, batch in [(64, 12, 1125899906826241, 5), (64, 11, 1125899906
     g = torch.empty_like(d); t.forward_batch_to(d, g); assert torch.equal(f, g)
     i = d.clone(); t.inverse_batch(i); out[key + "_inv"] = dig(i)
     c = torch.empty_like(d); t.polymul_batch(d, e, c); out[key + "_mul"] = dig(c)
+    if log_n == 14:   # in-place forms (the output parks fwd(a): aliasing rules of the stash / cluster kernels)
+        c1 = d.clone(); t.polymul_batch(c1, e, c1); assert torch.equal(c1, c)
+        c2 = e.clone(); t.polymul_batch(d, c2, c2); assert torch.equal(c2, c)
+        sq = torch.empty_like(d); t.polymul_batch(d, d, sq); c3 = d.clone(); t.polymul_batch(c3, c3, c3); assert torch.equal(c3, sq)
+        out[key + "_sq"] = dig(sq)
 # DCRT (per-limb tables) through the same kernels
 mods = [1125899906826241, 1125899906629633, 1125899904679937]
 dc = P.U64DcrtTable(12, mods)
@@ -98,7 +104,7 @@ def test_all_kernel_variants_agree_bit_for_bit():
     for env in ({"PFHE_NTT_TMA": "0"}, {"PFHE_F64_LAZY": "0"}, {"PFHE_DISABLE_F64": "1"}, {"PFHE_DISABLE_WIDE32": "1"},
                 {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}, {"PFHE_BR_FAST": "0"}, {"PFHE_BR_MINB": "5"}, {"PFHE_EP_FAST": "0"},
                 {"PFHE_POLYMUL_STASH": "0"}, {"PFHE_STAGE": "0"}, {"PFHE_DCRT_EP_TWO_KERNEL": "1"}, {"PFHE_EP_KEY_PREFETCH": "1"}, {"PFHE_EP_KEY_PREFETCH": "2"},
-                {"PFHE_DCRT_EP_FUSED_WIDE": "1"}):
+                {"PFHE_DCRT_EP_FUSED_WIDE": "1"}, {"PFHE_NTT_CLUSTER": "1"}):
         other = _run(env)
         diff = [k for k in base if base[k] != other[k]]
         assert not diff, (env, diff)
