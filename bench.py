@@ -724,10 +724,10 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
     # C3 RNS polynomial product: N=16384, 8 limbs of ~50-bit primes (q = 1 mod 2^15), fused per limb
     c3 = _c3_primes()
     dc = P.U64DcrtTable(14, c3, device=local_rank)
-    nrns = 512
+    nrns = 1024
     ra = torch.stack([torch.randint(0, m, (nrns, 16384), dtype=torch.int64, device="cuda", generator=g) for m in c3], dim=1).contiguous()
     rb, rc = ra.flip(0).contiguous(), torch.empty_like(ra)
-    dt = timed(lambda: dc.polymul_batch(ra, rb, rc))
+    dt = timed(lambda: dc.polymul_batch(ra, rb, rc), reps=5)
     extra["rns_polymuls_per_s_n16384_l8_u64"] = nrns / dt
     fp_limb = 3 * (8192 * 14 * 8 + 2 * 16384 * 3 + 16384 * 4) + 16384 * 12   # FP64 instructions of one limb product (3 transforms + pointwise)
     extra["rns_polymul_n16384_l8_roofline"] = dict(roof(nrns * 3 * 8 * 16384 * 8 / dt), bound="fp64 pipe (binding) / hbm",
