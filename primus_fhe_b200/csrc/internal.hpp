@@ -49,6 +49,7 @@ constexpr int kMaxLimbs = 16;
 template <typename T> struct LimbConsts {
     Barrett<T> br[kMaxLimbs];
     T scalar[kMaxLimbs], scalar_q[kMaxLimbs];
+    double q_f[kMaxLimbs], qinv_f[kMaxLimbs];  // filled by the slice-op launcher when the FP64 product applies (u64 words, q < 2^50)
 };
 // N = 16384 u64 FP64 transforms on a 2-CTA cluster (ntt_cluster.cu); mode 0 forward, 1 inverse, 2 fused product out = a * b
 cudaError_t launch_ntt_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, int mode, const uint64_t *a,

@@ -58,6 +58,11 @@ def test_slice_ops_match_oracle(bits, q, n):
     assert np.array_equal(_host(acc, dt), of.add_factor_mul_slice_assign(c.copy(), a))
     acc = _dev(c.copy()); gm.sub_factor_mul_slice_assign(s, acc, da)
     assert np.array_equal(_host(acc, dt), of.sub_factor_mul_slice_assign(c.copy(), a))
+    # a word that is not a canonical residue in an otherwise canonical vector: the double-word Barrett reduction still applies
+    # (barrett/mod.rs:99-139); the FP64 product of the u64 q < 2^50 path must hand that vector to the integer product
+    if n > 8 and q < (1 << (bits - 2)):
+        a2 = a.copy(); a2[5] = dt(q + 5); a2[6] = dt(2 * q - 1)
+        assert np.array_equal(_host(gm.reduce_mul_slice_to(_dev(a2), db, out), dt), om.reduce_mul_slice_to(a2, b))
     # in-place alias (mul_assign)
     ia = _dev(a.copy()); gm.reduce_mul_slice_assign(ia, db)
     assert np.array_equal(_host(ia, dt), om.reduce_mul_slice_to(a, b))
