@@ -158,7 +158,7 @@ template <int LOGE> struct Cl {
 template <int LOGE, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl<LOGE>::TPC, 2)
 ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *a, const T *b, T *out,
-                   size_t npolys) {  // out may alias a (in place): no __restrict__
+                   size_t npolys, unsigned stagger_ns) {  // out may alias a (in place): no __restrict__
     using C = Cl<LOGE>;
     using Core = typename C::Core;
     constexpr int E = C::E, TPC = C::TPC, FB0 = C::FB0;
@@ -170,6 +170,13 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
     const DevNtt<T> tb = limbs > 1 ? tables[poly % (size_t)limbs] : tb0;  // by value: only the fields in use occupy registers
     const F::Ctx c = F::ctx(tb);
     double x[E];
+    // The two CTAs that share an SM start together and take equally long, so without help they stay in phase (both loading, both
+    // computing, both storing) for the whole grid.  The clusters of the first wave therefore start with a pseudo-random delay of up to half a
+    // CTA lifetime; later waves inherit the offset.  (stagger_ns = 0 switches it off.)
+    if (stagger_ns && poly < 2 * 148) {
+        const unsigned steps = (unsigned)(((unsigned)poly * 2654435761u) >> 28);  // 0..15
+        for (unsigned i = 0; i < steps; i++) __nanosleep(stagger_ns);
+    }
     cluster_sync();  // the peer CTA is resident before its shared memory is addressed
     if (MODE == 0) {
         C::forward_g2r(a + poly * N, x, buf, tb, c, Tg, rank);
@@ -231,7 +238,8 @@ cudaError_t run_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tab
     cudaError_t e;
     auto go = [&](auto k) -> cudaError_t {
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, Cl<LOGE>::TPC, smem, s>>>(tb0, tables, limbs, a, b, out, npolys);
+        static const unsigned stagger = getenv("PFHE_NTT_CLUSTER_STAGGER_NS") ? (unsigned)atoi(getenv("PFHE_NTT_CLUSTER_STAGGER_NS")) : 1000u;
+        k<<<grid, Cl<LOGE>::TPC, smem, s>>>(tb0, tables, limbs, a, b, out, npolys, npolys > 2 * 148 ? stagger : 0u);  // one wave: nothing to de-phase
         count_launch();
         return cudaGetLastError();
     };
