@@ -88,6 +88,19 @@ for lb, lvl, nl in ((7, None, 24), (4, 5, 8), (1, 6, 8)):
     tv = torch.from_numpy(rng.integers(0, 132120577, 1024, dtype=np.uint64).astype(np.int64)).to(torch.int32).cuda()
     acc = torch.empty((5, 2048), dtype=torch.int32, device="cuda")
     t.blind_rotate_batch(lb, lvl, bsk, nl, lwe, tv, acc); out[f"br32_b{lb}"] = dig(acc)
+# pointwise product and base conversion: FP64-pipe formulations (u64 moduli below 2^50) vs the integer ones (PFHE_DISABLE_F64=1)
+Q50_, Q50B_, Q49_ = 1125899906826241, 1125899906629633, 562949953392641
+bm = P.BarrettModulus(Q50_, 64)
+xa = torch.from_numpy(rng.integers(0, Q50_, 4096, dtype=np.uint64).astype(np.int64)).cuda()
+xb = torch.from_numpy(rng.integers(0, Q50_, 4096, dtype=np.uint64).astype(np.int64)).cuda()
+xa[0] = Q50_ - 1; xb[0] = Q50_ - 1; xa[7] = Q50_ + 3      # one non-canonical word
+xo = torch.empty_like(xa); bm.reduce_mul_slice_to(xa, xb, xo); out["reduce_mul_q50"] = dig(xo)
+bcv = P.BaseConverter([Q50_, Q50B_, Q49_], [1125899904679937, 1125899905744897], 64)
+ci = torch.stack([torch.from_numpy(rng.integers(0, m, (3, 256), dtype=np.uint64).astype(np.int64)) for m in bcv.in_moduli], dim=1).contiguous().cuda()
+ci[0, 0, 0] = (1 << 63) - 1                                  # arbitrary word: reduced before the product
+co = torch.empty((3, 2, 256), dtype=torch.int64, device="cuda"); bcv.fast_convert_array(ci, co, 256); out["baseconv_fast"] = dig(co)
+bc1 = P.BaseConverter([Q50_, Q50B_, Q49_], [1125899904679937], 64)
+ce = torch.empty((3, 256), dtype=torch.int64, device="cuda"); bc1.exact_convert_array(ci, ce, 256); out["baseconv_exact"] = dig(ce)
 print("DIGESTS " + json.dumps(out))
 ''' % ROOT
 
