@@ -471,3 +471,57 @@ def test_ifma_restatement_matches_scalar_oracle():
             b = x.copy(); t.forward_batch_simd(b, 2)
             assert np.array_equal(a, b), (q, log_n)
     assert not O.U64NttTable(10, Q60).simd_supported()      # 60-bit primes are outside the BIT_SHIFT = 52 back-end
+
+
+def test_oracle_programmable_bootstrap_recovers_the_lookup_table_at_c5_parameters():
+    """Functional pin of the composed bootstrap (modulus switch -> blind rotation -> extract_lwe) at the BASELINE config-5 parameters: real
+    LWE / RGSW encryptions WITH noise, decrypted afterwards -- every message m must come back as LUT[m] with noise far below the decoding
+    margin.  The reference has no bootstrapping to compare with; this is the property its users rely on.  The GPU runs the same
+    flow in tests/test_gpu_bootstrap_functional.py."""
+    import bootstrap_common as B
+    t = O.U32NttTable(B.LOG_N, B.Q)
+    basis = O.ApproxSignedBasis(B.Q, B.LOG_B, None, 32)
+    lv, drop = basis.decompose_length(), basis.drop_bits()
+    rng = np.random.default_rng(20261018)
+    z, s = B.secrets(rng)
+    a1, e1 = B.rgsw_rows(rng, lv)
+    zrep = lambda rows: np.ascontiguousarray(np.broadcast_to(z.astype(np.uint32), rows.shape))
+    az = t.polymul_batch(a1.copy(), zrep(a1)).reshape(a1.shape)
+    key = np.ascontiguousarray(B.assemble_key(a1, az, e1, s, lv, drop).reshape(-1, B.N))
+    t.forward_batch(key)
+    batch = 6
+    msgs, lwe_q = B.lwe_inputs(rng, s, batch)
+    lwe_2n = O.modulus_switch(lwe_q, B.Q, B.LOG_N + 1)
+    ph2n = B.check_switched(lwe_2n, s, msgs)
+    acc = O.blind_rotate(t, basis, key.reshape(-1), B.N_LWE, lwe_2n, B.test_vector(), batch=batch).reshape(batch, 2, B.N)
+    out = np.stack([O.extract_lwe(acc[i].reshape(-1), B.Q, 32) for i in range(batch)])
+    a0 = np.ascontiguousarray(acc[:, 0])
+    worst = B.check_outputs(out, acc, t.polymul_batch(a0.copy(), zrep(a0)).reshape(a0.shape), z, msgs, ph2n)
+    assert worst > 0          # the keys really carried noise
+
+
+def test_oracle_ternary_bootstrap_recovers_the_lookup_table_at_c5_parameters():
+    """The same functional pin for the ternary-secret rotation by monomial combination: BSK+_i = RGSW([s_i = 1]),
+    BSK-_i = RGSW([s_i = -1]) with noise; the bootstrap must return LUT[m]."""
+    import bootstrap_common as B
+    t = O.U32NttTable(B.LOG_N, B.Q)
+    basis = O.ApproxSignedBasis(B.Q, B.LOG_B, None, 32)
+    lv, drop = basis.decompose_length(), basis.drop_bits()
+    rng = np.random.default_rng(77)
+    z, s = B.secrets(rng, ternary=True)
+    zrep = lambda rows: np.ascontiguousarray(np.broadcast_to(z.astype(np.uint32), rows.shape))
+    keys = []
+    for sign in (1, -1):
+        a1, e1 = B.rgsw_rows(rng, lv)
+        az = t.polymul_batch(a1.copy(), zrep(a1)).reshape(a1.shape)
+        k = np.ascontiguousarray(B.assemble_key(a1, az, e1, (s == sign).astype(np.int64), lv, drop).reshape(-1, B.N))
+        t.forward_batch(k)
+        keys.append(k.reshape(-1))
+    batch = 2
+    msgs, lwe_q = B.lwe_inputs(rng, s, batch)
+    lwe_2n = O.modulus_switch(lwe_q, B.Q, B.LOG_N + 1)
+    ph2n = B.check_switched(lwe_2n, s, msgs)
+    acc = O.blind_rotate_ternary(t, basis, keys[0], keys[1], B.N_LWE, lwe_2n, B.test_vector(), batch=batch).reshape(batch, 2, B.N)
+    out = np.stack([O.extract_lwe(acc[i].reshape(-1), B.Q, 32) for i in range(batch)])
+    a0 = np.ascontiguousarray(acc[:, 0])
+    B.check_outputs(out, acc, t.polymul_batch(a0.copy(), zrep(a0)).reshape(a0.shape), z, msgs, ph2n)
