@@ -525,3 +525,33 @@ def test_oracle_ternary_bootstrap_recovers_the_lookup_table_at_c5_parameters():
     out = np.stack([O.extract_lwe(acc[i].reshape(-1), B.Q, 32) for i in range(batch)])
     a0 = np.ascontiguousarray(acc[:, 0])
     B.check_outputs(out, acc, t.polymul_batch(a0.copy(), zrep(a0)).reshape(a0.shape), z, msgs, ph2n)
+
+
+@pytest.mark.parametrize("bits,moduli,log_n", [(32, [Q27], 11), (64, [Q50], 11), (64, [Q50, Q50B], 11)])
+def test_oracle_external_product_decrypts_to_the_product_at_c4_shapes(bits, moduli, log_n):
+    """Functional pin of the GGSW external product (a19 / a20) at the BASELINE config-4 degree: RLWE(m) [x] RGSW(mu) with real noisy
+    encryptions must decrypt to m * mu (mu = 1 + X^5 - X^100) -- single-word u32 / u64 gadget and the two-limb multi-word gadget."""
+    import extprod_common as X
+    dt = np.uint64 if bits == 64 else np.uint32
+    n, L = 1 << log_n, len(moduli)
+    tables = [(O.U64NttTable if bits == 64 else O.U32NttTable)(log_n, q) for q in moduli]
+    def ring_mul(i, rows, z):
+        zz = np.ascontiguousarray(np.broadcast_to(z.astype(dt), rows.shape))
+        return tables[i].polymul_batch(np.ascontiguousarray(rows).copy(), zz).reshape(rows.shape)
+    rng = np.random.default_rng(5)
+    if L == 1:
+        basis = O.ApproxSignedBasis(moduli[0], 7, None, bits)
+    else:
+        rns = O.RNSBase(moduli, bits); basis = O.BigUintApproxSignedBasis(rns, 7, None)
+    lv, drop = basis.decompose_length(), basis.drop_bits()
+    batch = 2 if L == 1 else 1
+    key, glwe, z, msg = X.rgsw_and_inputs(rng, moduli, n, lv, drop, 7, batch, ring_mul, dt)
+    for i in range(L):                                       # NTT form, limb by limb
+        rows = np.ascontiguousarray(key[:, :, :, i, :].reshape(-1, n))
+        tables[i].forward_batch(rows)
+        key[:, :, :, i, :] = rows.reshape(2, lv, 2, n)
+    if L == 1:
+        out = O.external_product_single(tables[0], basis, 1, key.reshape(-1), glwe.reshape(-1), to_coeff=True, batch=batch)
+    else:
+        out = O.external_product(O.DcrtTable(log_n, moduli, bits), rns, basis, 1, key.reshape(-1), glwe.reshape(-1), to_coeff=True, batch=batch)
+    X.check(np.asarray(out).reshape(batch, 2, L, n), moduli, z, msg, ring_mul)
