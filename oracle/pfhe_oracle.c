@@ -21,7 +21,12 @@
  *   (3) an independent pure-Python big-integer model (oracle/pymodel.py) and
  *       direct O(n^2) evaluation / schoolbook negacyclic products.
  * The NTT external product (no reference test at all) and blind rotation (not
- * in the reference) are "parity unpinned" at the composed level.
+ * in the reference) are "parity unpinned" at the composed level: no reference
+ * output exists to compare with.  What stands in for it (tests/test_oracle.py):
+ * the schoolbook identity at the BASELINE degrees, and functional tests with
+ * real noisy LWE / RLWE / RGSW encryptions -- RLWE(m) x RGSW(mu) decrypts to
+ * m * mu, and a programmable bootstrap returns LUT[m] -- at the config-4 / 5
+ * parameters (tests/extprod_common.py, tests/bootstrap_common.py).
  */
 #include <stdint.h>
 #include <stddef.h>
