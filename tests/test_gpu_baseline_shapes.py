@@ -128,6 +128,42 @@ def test_c3_dcrt_8_limbs_n16384():
     assert np.array_equal(c.cpu().numpy().view(np.uint64), mul)
 
 
+def test_c3_rns_product_is_the_big_integer_product():
+    """Independent of the oracle: the 8-limb N = 16384 RNS product, CRT-composed (RNSBase::compose on the GPU), equals the schoolbook negacyclic
+    product of the composed operands mod Q = prod q_i at sampled output coefficients (exact big-integer arithmetic)."""
+    import torch
+    import primus_fhe_b200 as P
+    mods = c3_primes()
+    n, L = 16384, 8
+    Q = 1
+    for m in mods:
+        Q *= m
+    rng = np.random.default_rng(81)
+    a = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])      # [L][n]
+    b = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])
+    gt = P.U64DcrtTable(14, mods)
+    c = torch.empty((1, L, n), dtype=torch.int64, device="cuda")
+    gt.polymul_batch(_dev(a[None].copy()), _dev(b[None].copy()), c)
+    rns = P.RNSBase(mods, 64)
+    vl = rns.big_uint_value_len()
+
+    def compose(res):                                                          # GPU compose -> python integers
+        big = torch.empty((n, vl), dtype=torch.int64, device="cuda")
+        rns.compose_multiple_values_to(_dev(np.ascontiguousarray(res)), big)
+        w = big.cpu().numpy().view(np.uint64)
+        return [sum(int(w[i, k]) << (64 * k) for k in range(vl)) for i in range(n)]
+
+    A, B_, C_ = compose(a), compose(b), compose(c.cpu().numpy().view(np.uint64)[0])
+    for i in range(L):                                                         # the composed operands really are the CRT lifts
+        assert A[5] % mods[i] == int(a[i, 5]) and B_[n - 1] % mods[i] == int(b[i, n - 1])
+    for j in (0, 1, 8191, n - 1):
+        acc = 0
+        for i in range(n):
+            k = j - i
+            acc += A[i] * B_[k] if k >= 0 else -A[i] * B_[k + n]
+        assert C_[j] == acc % Q, j
+
+
 def test_dcrt_mixed_50_and_60_bit_limbs():
     """A 50-bit limb next to a 60-bit limb: the whole launch runs on the integer pipe (one field policy per launch)."""
     import torch

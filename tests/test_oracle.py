@@ -555,3 +555,30 @@ def test_oracle_external_product_decrypts_to_the_product_at_c4_shapes(bits, modu
     else:
         out = O.external_product(O.DcrtTable(log_n, moduli, bits), rns, basis, 1, key.reshape(-1), glwe.reshape(-1), to_coeff=True, batch=batch)
     X.check(np.asarray(out).reshape(batch, 2, L, n), moduli, z, msg, ring_mul)
+
+
+def test_oracle_c3_rns_product_is_the_big_integer_product():
+    """BASELINE config 3 (8 limbs of ~50 bits, N = 16384), independent of any NTT: the per-limb products, CRT-composed, equal the schoolbook
+    negacyclic product of the composed operands mod Q at sampled coefficients (exact big-integer arithmetic)."""
+    from bench import _c3_primes
+    mods = _c3_primes(); n = 16384
+    Q = 1
+    for m in mods:
+        Q *= m
+    rng = np.random.default_rng(81)
+    a = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])
+    b = np.stack([rng.integers(0, m, n, dtype=np.uint64) for m in mods])
+    c = np.stack([O.U64NttTable(14, m).polymul_batch(a[i:i + 1].copy(), b[i:i + 1].copy(), 1).reshape(-1) for i, m in enumerate(mods)])
+    orns = O.RNSBase(mods, 64); vl = orns.big_uint_value_len()
+
+    def compose(res):
+        w = orns.compose_multiple_values_to(np.ascontiguousarray(res).reshape(-1), n).reshape(n, vl)
+        return [sum(int(w[i, k]) << (64 * k) for k in range(vl)) for i in range(n)]
+
+    A, B_, C_ = compose(a), compose(b), compose(c)
+    for j in (0, 1, 8191, n - 1):
+        acc = 0
+        for i in range(n):
+            k = j - i
+            acc += A[i] * B_[k] if k >= 0 else -A[i] * B_[k + n]
+        assert C_[j] == acc % Q, j
