@@ -6,7 +6,7 @@
 
 namespace pfhe {
 
-// ---- multi-limb external product in ONE kernel (composed values of at most two words) ------------------------------------------------
+// ---- multi-limb external product in ONE kernel (composed values of at most two words by default, up to four words opt-in) -------------
 // The digits of CrtGlwe::mul_dcrt_ggsw_to couple all limbs of a coefficient (compose -> multi-word gadget,
 // primus_lattice/src/glwe/dcrt.rs:219-236), which is why round 1 wrote them to HBM first (21 % of the product's time, profiles/
 // r02_large_n_experiments.md).  For Q below two words the coupling is cheap enough to repeat per limb: the CTA of (ciphertext, limb)

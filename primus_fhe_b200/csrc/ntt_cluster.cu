@@ -4,9 +4,11 @@
 // hold exactly ONE polynomial, so the load, FP64 and store phases of an SM never overlap (profiles/r02_ncu_ntt_fwd_n16384.txt: FP64 pipe
 // 57 %, 24 % of the stall samples wait for the loads, 17 % sit at EXIT).  Here a polynomial is split over the two CTAs of a cluster:
 // each CTA runs 256 of the 512 threads, keeps 32 doubles per thread and a 64 KiB buffer -- so TWO CTAs of different clusters are resident
-// per SM and one's memory phases hide behind the other's arithmetic.
+// per SM and one's memory phases hide behind the other's arithmetic.  Measured: +2..7 % on the transforms (default), the fused product is
+// faster cold and slower inside a long run (opt-in); the FP64 pipe stays at 57 % (profiles/r02_large_n_experiments.md).  The code is generic
+// over the register tile (Cl<5>: 2 x 256 threads x 32 words; Cl<4>: 2 x 512 threads x 16 words, measured slower).
 //
-// Index algebra (Plan<14, 5>: passes of 4 | 5 | 5 stages over index bits 13..10 | 9..5 | 4..0; T = cluster-wide thread id, 9 bits):
+// Index algebra for the default tile (Plan<14, 5>: passes of 4 | 5 | 5 stages over index bits 13..10 | 9..5 | 4..0; T = cluster-wide thread id, 9 bits):
 //   pass 0: thread T owns indices  j*512 + T            (j = index bits 13..9)
 //   pass 1: thread T owns indices  (T>>5)*1024 + j*32 + (T&31)
 //   pass 2: thread T owns indices  T*32 + j
