@@ -2,6 +2,7 @@
 include/pfhe.h declares, and reports the architecture it was compiled for.  No compute calls (no GPU here)."""
 import os
 import subprocess
+import pytest
 
 import primus_fhe_b200 as P
 
@@ -151,3 +152,29 @@ def test_rust_ffi_crate_bindings_are_complete_and_current():
         used = set(re.findall(r"\b(pfhe_[a-z0-9]+_[a-z0-9_]+)\b", open(os.path.join(root, "ffi", "primus_cuda", "src", f)).read()))
         used = {u for u in used if not re.fullmatch(r"pfhe_(ntt|dcrt|bsk|rns|baseconv|uintntt)(16|32|64)", u)} - {"pfhe_status", "pfhe_cuda", "pfhe_slice_op"}
         assert used <= declared, (f, used - declared)
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    import primus_fhe_b200 as P
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(P.LIB_PATH)
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-lpfhe_cuda", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/pfhe.h compiles as C11 with -Wall -Wextra -Werror, examples/c_abi_smoke.c links against the shared library with nothing but
+    the C runtime, and -- there being no GPU in the CPU test environment -- the product path fails loudly instead of falling back."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the run itself is covered by tests/test_gpu_ext.py")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "failed" in p.stderr and "smoke ok" not in p.stdout

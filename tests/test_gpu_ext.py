@@ -220,3 +220,13 @@ def test_registered_host_buffer_takes_the_direct_path():
     assert np.array_equal(staged, direct) and np.array_equal(direct[:4], want)
     with pytest.raises(P.PfheError):
         P.registered_host_buffer(np.empty(0, dtype=np.uint64)).__enter__()
+
+
+def test_c_program_drives_the_library_without_python(tmp_path):
+    """examples/c_abi_smoke.c: plain C against include/pfhe.h -- host slices round trip and a fused product, no torch in the process."""
+    import subprocess
+    from test_cabi import _build_c_example
+    exe = _build_c_example(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "c-abi smoke ok" in p.stdout
