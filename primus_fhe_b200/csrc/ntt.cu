@@ -750,11 +750,10 @@ cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint6
             case 13: return tb0.loge == 4 ? run_ntt<T, 13, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s)
                                           : run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 14: {
-                // 2-CTA cluster per polynomial (ntt_cluster.cu): two half-polynomial CTAs resident per SM.  Measured: +2..7 % on the transforms
-                // (9.52 M against 9.31 M NTT/s; 8-limb forward 0.38 against 0.36 of the HBM peak).  PFHE_NTT_CLUSTER=0 selects the
-                // one-CTA-per-polynomial kernels, =2 also runs the fused product on the cluster (faster cold -- 349 K against 301 K 8-limb
-                // products/s -- but with a spread down to 232 K inside a long run, so the stable one-CTA product stays the default)
-                static const bool cluster = env_int("PFHE_NTT_CLUSTER", 1) != 0 && env_int("PFHE_F64_LAZY", 1) != 0;
+                // 2-CTA cluster per polynomial (ntt_cluster.cu): two half-polynomial CTAs resident per SM, cross-CTA exchange by st.async +
+                // mbarriers.  Measured: forward 9.98 M against 9.32 M NTT/s, 8-limb fused product 353 K against 331 K (266 K inside the bench
+                // sequence).  PFHE_NTT_CLUSTER: 0 = one CTA per polynomial, 1 = transforms only, 2 (default) = transforms and fused product
+                static const bool cluster = env_int("PFHE_NTT_CLUSTER", 2) != 0 && env_int("PFHE_F64_LAZY", 1) != 0;
                 if (cluster) {
                     const cudaError_t ce = launch_ntt_cluster(tb0, tables, limbs, fwd ? 0 : 1, src, nullptr, dst, npolys, s);
                     if (ce != cudaErrorNotSupported) return ce;
@@ -809,7 +808,7 @@ cudaError_t launch_polymul<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<u
             case 13: return tb0.loge == 4 ? run_polymul<T, 13, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s)
                                           : run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
             case 14: {
-                static const bool cluster = env_int("PFHE_NTT_CLUSTER", 1) == 2 && env_int("PFHE_F64_LAZY", 1) != 0;
+                static const bool cluster = env_int("PFHE_NTT_CLUSTER", 2) == 2 && env_int("PFHE_F64_LAZY", 1) != 0;
                 if (cluster && !(c == b && c == a)) {  // the parked fwd(a) lives in c: c == b swaps the (commuting) operands, a == b == c cannot park
                     const bool swap = c == b;
                     const cudaError_t ce = launch_ntt_cluster(tb0, tables, limbs, 2, swap ? b : a, swap ? a : b, c, npolys, s);

@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "internal.hpp"
+#include "tma.cuh"
 
 namespace pfhe {
 
@@ -40,6 +41,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void st_cluster(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+// asynchronous remote store that signals `bytes written` on an mbarrier of the destination CTA (no fence, no L1 invalidation on the reader side)
+__device__ __forceinline__ void st_async_cluster(uint32_t addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr), "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
 
 using F = F64LazyField;
 using T = uint64_t;
@@ -90,6 +97,78 @@ template <int LOGE> struct Cl {
             local_sync<PASS>();
             fwd_local<PASS + 1>(x, buf, tb, c, Tg);
         }
+    }
+    // ---- cross-CTA exchange by st.async + mbarriers (default): no cluster barrier, no fence, no L1 invalidation per exchange ------------------
+    // Each CTA owns two mbarriers (count 1): `full` counts the bytes the peer writes into this CTA's buffer (st.async complete_tx; the one
+    // arrival is this CTA's expect_tx), `ready` is arrived on REMOTELY by the peer when the peer's buffer may be overwritten.
+    struct Xchg {
+        uint64_t *full, *ready;
+        uint32_t full_phase, ready_phase, peer_buf, peer_full, peer_ready;
+        bool first;  // the first exchange of a kernel needs no `ready` handshake (buffers are free after the start barrier)
+    };
+    __device__ __forceinline__ static Xchg xchg_make(double *buf, uint64_t *bars, uint32_t rank) {
+        Xchg xs;
+        xs.full = bars;
+        xs.ready = bars + 1;
+        xs.full_phase = xs.ready_phase = 0u;
+        xs.peer_buf = map_to_cta(smem_u32(buf), rank ^ 1u);
+        xs.peer_full = map_to_cta(smem_u32(bars), rank ^ 1u);
+        xs.peer_ready = map_to_cta(smem_u32(bars + 1), rank ^ 1u);
+        xs.first = true;
+        return xs;
+    }
+    // Call when every thread of this CTA has finished reading the buffer's current contents.  Afterwards the local half may be overwritten
+    // at once and the peer's half once the peer has said the same about its buffer.
+    __device__ __forceinline__ static void xchg_begin(Xchg &xs) {
+        if (!xs.first) __syncthreads();
+        if (threadIdx.x == 0) {
+            if (!xs.first)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(xs.peer_ready) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(xs.full)), "r"((uint32_t)(TPC * (E / 2) * 8)) : "memory");
+        }
+        if (!xs.first) {
+            mbar_wait(xs.ready, xs.ready_phase);
+            xs.ready_phase ^= 1u;
+        }
+        xs.first = false;
+    }
+    __device__ __forceinline__ static void xchg_end(Xchg &xs) {
+        __syncthreads();                     // this CTA's own half is in place
+        mbar_wait(xs.full, xs.full_phase);   // the peer's half has landed
+        xs.full_phase ^= 1u;
+    }
+    __device__ __forceinline__ static void forward_g2r_async(const T *g, double (&x)[E], double *buf, Xchg &xs, const DevNtt<T> &tb, const F::Ctx &c,
+                                                             int Tg, uint32_t rank) {
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = F::load(ldg_stream(g + Core::elem_index(FB0, Tg, j)), c);
+        Core::template fwd_pass_regs<0>(x, tb, c, Tg);
+        xchg_begin(xs);
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+            const int idx = Core::elem_index(FB0, Tg, j);
+            if ((uint32_t)(j >> (LOGE - 1)) == rank) buf[lswz(idx)] = x[j];
+            else st_async_cluster(xs.peer_buf + 8u * (uint32_t)lswz(idx), x[j], xs.peer_full);
+        }
+        xchg_end(xs);
+        fwd_local<1>(x, buf, tb, c, Tg);
+    }
+    __device__ __forceinline__ static void inverse_r2r_async(double (&x)[E], double *buf, Xchg &xs, const DevNtt<T> &tb, const F::Ctx &c, int Tg,
+                                                             uint32_t rank) {
+        inv_local<NPASS - 1>(x, buf, tb, c, Tg);  // ends with the pass-1 outputs in registers
+        xs.first = false;                         // the buffers have been in use: always handshake
+        xchg_begin(xs);
+#pragma unroll
+        for (int j = 0; j < E; j++) {
+            const int i = Core::elem_index(P::fb(1), Tg, j);
+            const uint32_t owner = (uint32_t)(i >> LOG_TPC) & 1u;
+            const int slot = ((i >> FB0) << LOG_TPC) | (i & (TPC - 1));
+            if (owner == rank) buf[slot] = x[j];
+            else st_async_cluster(xs.peer_buf + 8u * (uint32_t)slot, x[j], xs.peer_full);
+        }
+        xchg_end(xs);
+#pragma unroll
+        for (int j = 0; j < E; j++) x[j] = buf[(j << LOG_TPC) | (Tg & (TPC - 1))];
+        Core::template inv_pass_regs<0>(x, tb, c, Tg);
     }
     // forward: global (natural order) -> registers of the last pass (lazy form); Tg = cluster-wide thread id, buf = this CTA's 64 KiB buffer
     __device__ __forceinline__ static void forward_g2r(const T *g, double (&x)[E], double *buf, const DevNtt<T> &tb, const F::Ctx &c, int Tg,
@@ -157,7 +236,8 @@ template <int LOGE> struct Cl {
 };
 
 // MODE 0: forward, 1: inverse, 2: fused product c = a * b (fwd(a) parked in the output polynomial, as in polymul_kernel<STASH>)
-template <int LOGE, int MODE>
+// ASYNC: cross-CTA exchanges by st.async + mbarriers (default); otherwise st.shared::cluster + barrier.cluster (PFHE_NTT_CLUSTER_ASYNC=0)
+template <int LOGE, int MODE, bool ASYNC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl<LOGE>::TPC, 2)
 ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *a, const T *b, T *out,
                    size_t npolys, unsigned stagger_ns) {  // out may alias a (in place): no __restrict__
@@ -166,6 +246,7 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
     constexpr int E = C::E, TPC = C::TPC, FB0 = C::FB0;
     extern __shared__ __align__(16) unsigned char smem_c[];
     double *buf = reinterpret_cast<double *>(smem_c);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_c + sizeof(double) * HALF);  // ASYNC: full, ready
     const uint32_t rank = cluster_rank();
     const int t = threadIdx.x, Tg = (int)rank * TPC + t;
     const size_t poly = blockIdx.x >> 1;
@@ -179,9 +260,24 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
         const unsigned steps = (unsigned)(((unsigned)poly * 2654435761u) >> 28);  // 0..15
         for (unsigned i = 0; i < steps; i++) __nanosleep(stagger_ns);
     }
-    cluster_sync();  // the peer CTA is resident before its shared memory is addressed
+    if (ASYNC && t == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+    }
+    cluster_sync();  // the peer CTA is resident (and its mbarriers initialised) before its shared memory is addressed
+    typename C::Xchg xs = C::xchg_make(buf, bars, rank);
+    auto forward = [&](const T *g, double *bf, int tg) {
+        if constexpr (ASYNC) C::forward_g2r_async(g, x, bf, xs, tb, c, tg, rank);
+        else C::forward_g2r(g, x, bf, tb, c, tg, rank);
+    };
+    auto inverse = [&](double *bf, int tg) {
+        if constexpr (ASYNC) C::inverse_r2r_async(x, bf, xs, tb, c, tg, rank);
+        else C::inverse_r2r(x, bf, tb, c, tg, rank);
+    };
+    // Exit needs no further cluster barrier in the ASYNC form: every remote store INTO this CTA had landed when its last wait returned, and
+    // the peer -- the destination of this CTA's remote stores and remote arrivals -- cannot leave before they land because it waits for them.
     if (MODE == 0) {
-        C::forward_g2r(a + poly * N, x, buf, tb, c, Tg, rank);
+        forward(a + poly * N, buf, Tg);
 #pragma unroll
         for (int j = 0; j < E; j++) x[j] = F::fwd_bits(x[j], c);
         C::template store_pass<C::NPASS - 1>(x, buf, Tg);
@@ -193,12 +289,12 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
         C::template load_pass<C::NPASS - 1>(x, buf, Tg);
 #pragma unroll
         for (int j = 0; j < E; j++) x[j] = F::load_bits(x[j], c);
-        C::inverse_r2r(x, buf, tb, c, Tg, rank);
+        inverse(buf, Tg);
 #pragma unroll
         for (int j = 0; j < E; j++) stg_stream(out + poly * N + Core::elem_index(FB0, Tg, j), F::inv_word(x[j], c));
     } else {
         T *g_c = out + poly * N;
-        C::forward_g2r(a + poly * N, x, buf, tb, c, Tg, rank);
+        forward(a + poly * N, buf, Tg);
         // fwd(a), canonical, parked in this thread's own contiguous words of the output polynomial (read back by the same thread)
         T *mine_c = g_c + (size_t)Tg * E;
 #pragma unroll
@@ -208,13 +304,13 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
             raw.x = (uint32_t)w0; raw.y = (uint32_t)(w0 >> 32); raw.z = (uint32_t)w1; raw.w = (uint32_t)(w1 >> 32);
             *reinterpret_cast<uint4 *>(mine_c + v * CW) = raw;
         }
-        cluster_sync();  // both CTAs are done with the last-pass reads of their buffers before the next transform's exchange writes into them
+        if constexpr (!ASYNC) cluster_sync();  // both CTAs are done with the last-pass reads of their buffers before the next exchange writes into them
         // the second transform uses the same thread id: hide that from the compiler, which would otherwise keep every shared-memory / peer
         // address of the first transform alive for reuse (common-subexpression elimination) and spill them -- recomputing is 2-3 ALU ops
         int Tg2 = Tg;
         double *buf2 = buf;
         asm volatile("" : "+r"(Tg2), "+l"(buf2));
-        C::forward_g2r(b + poly * N, x, buf2, tb, c, Tg2, rank);
+        forward(b + poly * N, buf2, Tg2);
 #pragma unroll
         for (int v = 0; v < E / CW; v++) {
             uint4 raw;  // written above by this thread (program order); volatile: a few 16-byte loads in flight at a time
@@ -226,7 +322,7 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
         int Tg3 = Tg;
         double *buf3 = buf;
         asm volatile("" : "+r"(Tg3), "+l"(buf3));
-        C::inverse_r2r(x, buf3, tb, c, Tg3, rank);
+        inverse(buf3, Tg3);
 #pragma unroll
         for (int j = 0; j < E; j++) stg_stream(g_c + Core::elem_index(FB0, Tg3, j), F::inv_word(x[j], c));
     }
@@ -235,7 +331,7 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
 template <int LOGE>
 cudaError_t run_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, int mode, const uint64_t *a, const uint64_t *b,
                         uint64_t *out, size_t npolys, cudaStream_t s) {
-    constexpr size_t smem = sizeof(double) * HALF;
+    constexpr size_t smem = sizeof(double) * HALF + 16;  // + two mbarriers (st.async variant)
     const unsigned grid = (unsigned)(2 * npolys);
     cudaError_t e;
     auto go = [&](auto k) -> cudaError_t {
@@ -245,9 +341,15 @@ cudaError_t run_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tab
         count_launch();
         return cudaGetLastError();
     };
-    if (mode == 0) return go(ntt_cluster_kernel<LOGE, 0>);
-    if (mode == 1) return go(ntt_cluster_kernel<LOGE, 1>);
-    return go(ntt_cluster_kernel<LOGE, 2>);
+    static const bool async = !(getenv("PFHE_NTT_CLUSTER_ASYNC") && getenv("PFHE_NTT_CLUSTER_ASYNC")[0] == '0');
+    if (async) {
+        if (mode == 0) return go(ntt_cluster_kernel<LOGE, 0, true>);
+        if (mode == 1) return go(ntt_cluster_kernel<LOGE, 1, true>);
+        return go(ntt_cluster_kernel<LOGE, 2, true>);
+    }
+    if (mode == 0) return go(ntt_cluster_kernel<LOGE, 0, false>);
+    if (mode == 1) return go(ntt_cluster_kernel<LOGE, 1, false>);
+    return go(ntt_cluster_kernel<LOGE, 2, false>);
 }
 
 }  // namespace
