@@ -733,7 +733,7 @@ def bench_extra(P, torch, np, table, data, g, local_rank, peak, extra, checks):
     extra["rns_polymul_n16384_l8_roofline"] = dict(roof(nrns * 3 * 8 * 16384 * 8 / dt), bound="fp64 pipe (binding) / hbm",
                                                    algorithmic_bytes_per_product=3 * 8 * 16384 * 8, fp64_instr_per_limb_product=fp_limb,
                                                    frac_of_fp64_pipe=nrns * 8 / dt * fp_limb / FP64_PEAK,
-                                                   note="one polynomial per SM (register file and shared memory full): see profiles/r02_large_n_experiments.md")
+                                                   note="2-CTA thread-block cluster per polynomial, st.async exchange (ntt_cluster.cu); history in profiles/r02_large_n_experiments.md")
     want = np.stack([O.U64NttTable(14, m).polymul_batch(u64(ra[:1, i]).copy(), u64(rb[:1, i]).copy(), 1) for i, m in enumerate(c3)], axis=1)
     checks["rns_polymul_n16384_l8"] = bool(np.array_equal(u64(rc[:1]), want))
     fa = ra.clone()

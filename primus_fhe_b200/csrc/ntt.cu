@@ -747,8 +747,15 @@ cudaError_t launch_ntt<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<uint6
             case 10: return run_ntt<T, 10, 5, 4>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 11: return run_ntt<T, 11, 4, 2>(tb0, tables, limbs, src, dst, npolys, fwd, s);
             case 12: return run_ntt<T, 12, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
-            case 13: return tb0.loge == 4 ? run_ntt<T, 13, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s)
-                                          : run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            case 13: {
+                static const bool cluster13 = env_int("PFHE_NTT_CLUSTER13", 0) != 0 && env_int("PFHE_F64_LAZY", 1) != 0;  // N = 8192 on the cluster kernels
+                if (cluster13) {
+                    const cudaError_t ce = launch_ntt_cluster(tb0, tables, limbs, fwd ? 0 : 1, src, nullptr, dst, npolys, s);
+                    if (ce != cudaErrorNotSupported) return ce;
+                }
+                return tb0.loge == 4 ? run_ntt<T, 13, 4, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s)
+                                     : run_ntt<T, 13, 5, 1>(tb0, tables, limbs, src, dst, npolys, fwd, s);
+            }
             case 14: {
                 // 2-CTA cluster per polynomial (ntt_cluster.cu): two half-polynomial CTAs resident per SM, cross-CTA exchange by st.async +
                 // mbarriers.  Measured: forward 9.98 M against 9.32 M NTT/s, 8-limb fused product 353 K against 331 K (266 K inside the bench
@@ -805,8 +812,16 @@ cudaError_t launch_polymul<uint64_t>(const DevNtt<uint64_t> &tb0, const DevNtt<u
             case 10: return run_polymul<T, 10, 5, 4>(tb0, tables, limbs, a, b, c, npolys, s);
             case 11: return run_polymul<T, 11, 4, 2>(tb0, tables, limbs, a, b, c, npolys, s);
             case 12: return run_polymul<T, 12, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s);
-            case 13: return tb0.loge == 4 ? run_polymul<T, 13, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s)
-                                          : run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            case 13: {
+                static const bool cluster13 = env_int("PFHE_NTT_CLUSTER13", 0) == 2 && env_int("PFHE_F64_LAZY", 1) != 0;
+                if (cluster13 && !(c == b && c == a)) {
+                    const bool swap = c == b;
+                    const cudaError_t ce = launch_ntt_cluster(tb0, tables, limbs, 2, swap ? b : a, swap ? a : b, c, npolys, s);
+                    if (ce != cudaErrorNotSupported) return ce;
+                }
+                return tb0.loge == 4 ? run_polymul<T, 13, 4, 1>(tb0, tables, limbs, a, b, c, npolys, s)
+                                     : run_polymul<T, 13, 5, 1>(tb0, tables, limbs, a, b, c, npolys, s);
+            }
             case 14: {
                 static const bool cluster = env_int("PFHE_NTT_CLUSTER", 2) == 2 && env_int("PFHE_F64_LAZY", 1) != 0;
                 if (cluster && !(c == b && c == a)) {  // the parked fwd(a) lives in c: c == b swaps the (commuting) operands, a == b == c cannot park

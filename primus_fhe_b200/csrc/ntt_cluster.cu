@@ -1,12 +1,15 @@
-// ntt_cluster.cu -- N = 16384 transforms (u64 words, q < 2^50, FP64 lazy-fold butterflies) on a 2-CTA thread-block cluster.
+// ntt_cluster.cu -- N = 16384 transforms and fused products (u64 words, q < 2^50, FP64 lazy-fold butterflies) on a 2-CTA thread-block cluster.
 //
 // Why: with one CTA per polynomial the register file (512 threads x 32 doubles) and shared memory (one 128 KiB exchange buffer) of an SM
 // hold exactly ONE polynomial, so the load, FP64 and store phases of an SM never overlap (profiles/r02_ncu_ntt_fwd_n16384.txt: FP64 pipe
 // 57 %, 24 % of the stall samples wait for the loads, 17 % sit at EXIT).  Here a polynomial is split over the two CTAs of a cluster:
 // each CTA runs 256 of the 512 threads, keeps 32 doubles per thread and a 64 KiB buffer -- so TWO CTAs of different clusters are resident
-// per SM and one's memory phases hide behind the other's arithmetic.  Measured: +2..7 % on the transforms (default), the fused product is
-// faster cold and slower inside a long run (opt-in); the FP64 pipe stays at 57 % (profiles/r02_large_n_experiments.md).  The code is generic
-// over the register tile (Cl<5>: 2 x 256 threads x 32 words; Cl<4>: 2 x 512 threads x 16 words, measured slower).
+// per SM and one's memory phases hide behind the other's arithmetic.  The one exchange that crosses the pair uses st.async with
+// mbarrier::complete_tx on the destination CTA's mbarrier and a remote mbarrier.arrive as the "buffer free" signal: no cluster barrier, no
+// GPU-scope fence and no L1 invalidation per exchange (the barrier.cluster form is kept behind PFHE_NTT_CLUSTER_ASYNC=0).
+// Measured (profiles/r02_cluster_ntt_ab.log): forward 9.98 M against 9.32 M NTT/s, 8-limb fused product 353 K against 331 K (266 K inside the
+// bench sequence).  The code is generic over the degree and the register tile -- Cl<14, 5>: 2 x 256 threads x 32 words (default);
+// Cl<14, 4>: 2 x 512 x 16 and Cl<13, 5>: N = 8192, 2 x 128 x 32 were measured slower than their one-CTA kernels (opt-in).
 //
 // Index algebra for the default tile (Plan<14, 5>: passes of 4 | 5 | 5 stages over index bits 13..10 | 9..5 | 4..0; T = cluster-wide thread id, 9 bits):
 //   pass 0: thread T owns indices  j*512 + T            (j = index bits 13..9)
@@ -14,7 +17,7 @@
 //   pass 2: thread T owns indices  T*32 + j
 // CTA c runs the threads with T>>8 == c.  From pass 1 on a thread's indices all have bit 13 == c, so CTA c's buffer holds the index range
 // [c*8192, (c+1)*8192) and the exchange between passes 1 and 2 is CTA-local (and warp-local).  Only the exchange between passes 0 and 1
-// crosses the pair: a thread stores its words with j < 16 into CTA 0's buffer and those with j >= 16 into CTA 1's (st.shared::cluster).
+// crosses the pair: a thread stores its words with j < 16 into CTA 0's buffer and those with j >= 16 into CTA 1's.
 // The inverse transform mirrors this with a pass-0 buffer laid out as [k][T & 255] per CTA.
 #include <cstdlib>
 
@@ -50,16 +53,17 @@ __device__ __forceinline__ void st_async_cluster(uint32_t addr, double v, uint32
 
 using F = F64LazyField;
 using T = uint64_t;
-constexpr int LOGN = 14, N = 1 << LOGN, HALF = N / 2, CW = 2;
+constexpr int CW = 2;
 
 // LOGE = 5: 2 x 256 threads x 32 words (128 registers, 16 warps per SM); LOGE = 4: 2 x 512 threads x 16 words (64 registers, 32 warps per SM)
-template <int LOGE> struct Cl {
+template <int LOGN, int LOGE> struct Cl {
+    static constexpr int N = 1 << LOGN, HALF = N / 2;
     using Core = NttCore<F, LOGN, LOGE>;
     using P = typename Core::P;
     static constexpr int E = 1 << LOGE, TPC = (N / E) / 2, LOG_TPC = LOGN - LOGE - 1, FB0 = P::fb(0), NPASS = P::NPASS;
     static_assert(FB0 == LOGN - LOGE && P::fb(1) + LOGE <= LOGN - 1, "from pass 1 on a thread's indices must stay inside one half of the index space");
 
-    // The exchange-buffer swizzle of NttCore never touches index bit 13, so a CTA-local buffer addressed with (index & 8191) keeps the
+    // The exchange-buffer swizzle of NttCore never touches the top index bit, so a CTA-local buffer addressed with (index & (N/2 - 1)) keeps the
     // conflict-free patterns of the single-CTA kernels.
     __device__ __forceinline__ static int lswz(int idx) { return Core::swz(idx) & (HALF - 1); }
 
@@ -237,16 +241,16 @@ template <int LOGE> struct Cl {
 
 // MODE 0: forward, 1: inverse, 2: fused product c = a * b (fwd(a) parked in the output polynomial, as in polymul_kernel<STASH>)
 // ASYNC: cross-CTA exchanges by st.async + mbarriers (default); otherwise st.shared::cluster + barrier.cluster (PFHE_NTT_CLUSTER_ASYNC=0)
-template <int LOGE, int MODE, bool ASYNC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl<LOGE>::TPC, 2)
+template <int LOGN, int LOGE, int MODE, bool ASYNC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cl<LOGN, LOGE>::TPC, 512 / Cl<LOGN, LOGE>::TPC)
 ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__restrict__ tables, int limbs, const T *a, const T *b, T *out,
                    size_t npolys, unsigned stagger_ns) {  // out may alias a (in place): no __restrict__
-    using C = Cl<LOGE>;
+    using C = Cl<LOGN, LOGE>;
     using Core = typename C::Core;
-    constexpr int E = C::E, TPC = C::TPC, FB0 = C::FB0;
+    constexpr int E = C::E, TPC = C::TPC, FB0 = C::FB0, N = C::N, HALF = C::HALF;
     extern __shared__ __align__(16) unsigned char smem_c[];
     double *buf = reinterpret_cast<double *>(smem_c);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_c + sizeof(double) * HALF);  // ASYNC: full, ready
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_c + sizeof(double) * C::HALF);  // ASYNC: full, ready
     const uint32_t rank = cluster_rank();
     const int t = threadIdx.x, Tg = (int)rank * TPC + t;
     const size_t poly = blockIdx.x >> 1;
@@ -328,28 +332,28 @@ ntt_cluster_kernel(const __grid_constant__ DevNtt<T> tb0, const DevNtt<T> *__res
     }
 }
 
-template <int LOGE>
+template <int LOGN, int LOGE>
 cudaError_t run_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, int mode, const uint64_t *a, const uint64_t *b,
                         uint64_t *out, size_t npolys, cudaStream_t s) {
-    constexpr size_t smem = sizeof(double) * HALF + 16;  // + two mbarriers (st.async variant)
+    constexpr size_t smem = sizeof(double) * Cl<LOGN, LOGE>::HALF + 16;  // + two mbarriers (st.async variant)
     const unsigned grid = (unsigned)(2 * npolys);
     cudaError_t e;
     auto go = [&](auto k) -> cudaError_t {
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         static const unsigned stagger = getenv("PFHE_NTT_CLUSTER_STAGGER_NS") ? (unsigned)atoi(getenv("PFHE_NTT_CLUSTER_STAGGER_NS")) : 1000u;
-        k<<<grid, Cl<LOGE>::TPC, smem, s>>>(tb0, tables, limbs, a, b, out, npolys, npolys > 2 * 148 ? stagger : 0u);  // one wave: nothing to de-phase
+        k<<<grid, Cl<LOGN, LOGE>::TPC, smem, s>>>(tb0, tables, limbs, a, b, out, npolys, npolys > 2 * 148 ? stagger : 0u);  // one wave: nothing to de-phase
         count_launch();
         return cudaGetLastError();
     };
     static const bool async = !(getenv("PFHE_NTT_CLUSTER_ASYNC") && getenv("PFHE_NTT_CLUSTER_ASYNC")[0] == '0');
     if (async) {
-        if (mode == 0) return go(ntt_cluster_kernel<LOGE, 0, true>);
-        if (mode == 1) return go(ntt_cluster_kernel<LOGE, 1, true>);
-        return go(ntt_cluster_kernel<LOGE, 2, true>);
+        if (mode == 0) return go(ntt_cluster_kernel<LOGN, LOGE, 0, true>);
+        if (mode == 1) return go(ntt_cluster_kernel<LOGN, LOGE, 1, true>);
+        return go(ntt_cluster_kernel<LOGN, LOGE, 2, true>);
     }
-    if (mode == 0) return go(ntt_cluster_kernel<LOGE, 0, false>);
-    if (mode == 1) return go(ntt_cluster_kernel<LOGE, 1, false>);
-    return go(ntt_cluster_kernel<LOGE, 2, false>);
+    if (mode == 0) return go(ntt_cluster_kernel<LOGN, LOGE, 0, false>);
+    if (mode == 1) return go(ntt_cluster_kernel<LOGN, LOGE, 1, false>);
+    return go(ntt_cluster_kernel<LOGN, LOGE, 2, false>);
 }
 
 }  // namespace
@@ -357,10 +361,11 @@ cudaError_t run_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tab
 // cudaErrorNotSupported unless the table is a u64 FP64 lazy-fold N = 16384 layout (16- or 32-word register tiles)
 cudaError_t launch_ntt_cluster(const DevNtt<uint64_t> &tb0, const DevNtt<uint64_t> *tables, int limbs, int mode, const uint64_t *a,
                                const uint64_t *b, uint64_t *out, size_t npolys, cudaStream_t s) {
-    if (tb0.log_n != LOGN || (tb0.loge != 4 && tb0.loge != 5) || !tb0.use_f64) return cudaErrorNotSupported;
+    if (!tb0.use_f64 || !((tb0.log_n == 14 && (tb0.loge == 4 || tb0.loge == 5)) || (tb0.log_n == 13 && tb0.loge == 5))) return cudaErrorNotSupported;
     if (npolys == 0) return cudaSuccess;
     if (npolys > 0x3fffffffu) return cudaErrorNotSupported;
-    return tb0.loge == 4 ? run_cluster<4>(tb0, tables, limbs, mode, a, b, out, npolys, s) : run_cluster<5>(tb0, tables, limbs, mode, a, b, out, npolys, s);
+    if (tb0.log_n == 13) return run_cluster<13, 5>(tb0, tables, limbs, mode, a, b, out, npolys, s);
+    return tb0.loge == 4 ? run_cluster<14, 4>(tb0, tables, limbs, mode, a, b, out, npolys, s) : run_cluster<14, 5>(tb0, tables, limbs, mode, a, b, out, npolys, s);
 }
 
 }  // namespace pfhe

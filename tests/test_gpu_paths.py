@@ -117,7 +117,7 @@ def test_all_kernel_variants_agree_bit_for_bit():
     for env in ({"PFHE_NTT_TMA": "0"}, {"PFHE_F64_LAZY": "0"}, {"PFHE_DISABLE_F64": "1"}, {"PFHE_DISABLE_WIDE32": "1"},
                 {"PFHE_NTT_TMA": "0", "PFHE_DISABLE_F64": "1"}, {"PFHE_BR_FAST": "0"}, {"PFHE_BR_MINB": "5"}, {"PFHE_EP_FAST": "0"},
                 {"PFHE_POLYMUL_STASH": "0"}, {"PFHE_STAGE": "0"}, {"PFHE_DCRT_EP_TWO_KERNEL": "1"}, {"PFHE_EP_KEY_PREFETCH": "1"}, {"PFHE_EP_KEY_PREFETCH": "2"},
-                {"PFHE_DCRT_EP_FUSED_WIDE": "1"}, {"PFHE_NTT_CLUSTER": "0"}, {"PFHE_NTT_CLUSTER": "1"}, {"PFHE_NTT_CLUSTER_STAGGER_NS": "0"}, {"PFHE_NTT_CLUSTER_ASYNC": "0"}):
+                {"PFHE_DCRT_EP_FUSED_WIDE": "1"}, {"PFHE_NTT_CLUSTER": "0"}, {"PFHE_NTT_CLUSTER": "1"}, {"PFHE_NTT_CLUSTER_STAGGER_NS": "0"}, {"PFHE_NTT_CLUSTER_ASYNC": "0"}, {"PFHE_NTT_CLUSTER13": "2"}):
         other = _run(env)
         diff = [k for k in base if base[k] != other[k]]
         assert not diff, (env, diff)
