@@ -397,7 +397,8 @@ template <> __device__ __forceinline__ uint64_t double_to_word<uint64_t>(double 
 // polynomial length is a power of two (log_n >= 0), by one 64-bit division otherwise.
 // F64 (u64 words, every modulus below 2^50 - 2^10): all modular products run on the FP64 pipe -- x*inv mod q_i and y_i * (Q/q_i mod p_k) mod p_k
 // are exact-integer-in-a-double products (6 instructions, |result| <= 0.75 p: the quotient estimate of a product below 2^100 is off by at
-// most 0.25 + the rounding to an integer), the <= 8 terms per output sum exactly (6 p < 2^53) and one fold gives the canonical residue.  The
+// most 0.25 + the rounding to an integer), the <= 8 terms per output sum exactly (6.5 p < 2^53, walked with exact rationals by
+// tools/f64_bounds.py::canonical_product_budget) and one fold gives the canonical residue.  The
 // integer formulation needs ~28 64-bit multiplies per coefficient of a 3 -> 2 conversion (0.31 of the HBM copy peak, integer-issue bound);
 // the FP64 one 86 FP64 instructions (HBM bound).  An input word >= 2^50 (not a canonical residue) takes the integer path for that term.
 template <typename T, int NIN, bool EXACT, bool F64>

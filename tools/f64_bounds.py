@@ -86,6 +86,32 @@ def mac_budget(q, every=8):
     return float(max(first, later) / q)
 
 
+def canonical_product_budget(qs_in, ps_out):
+    """Round-2 uses of the same product outside the transforms (rns.cu baseconv_kernel<F64>, pointwise.cu f64_mul_canonical):
+    operands are CANONICAL residues (0 <= y < q_i <= QMAX, multiplier below the modulus of the product), level 0.
+      base conversion:  y_i = x_i * inv_i mod q_i   (|result| < q_i, made canonical by one conditional + q_i)
+                        out_k = sum_i y_i * M[k][i] mod p_k,  y_i < q_i (NOT reduced mod p_k), M < p_k: at most 8 terms, then one fold
+                        exact variant: minus v * (Q mod p_k), v <= 8
+      reduce_mul:       a * b mod q with a, b < q, result + q in (0, 2q), one conditional subtraction."""
+    worst = Fr(0)
+    for q in qs_in:
+        t = mul_bound(Fr(q), 0, Fr(q))           # x < q (non-canonical words are reduced first), inv < q
+        assert t < q                              # so  v < 0 ? v + q : v  is the canonical residue
+        worst = max(worst, t / q)
+    for p in ps_out:
+        acc = Fr(0)
+        for q in qs_in[:8]:
+            acc += mul_bound(Fr(q), 0, Fr(p))     # |y_i * M mod p| with y_i < q_i <= QMAX
+        acc += mul_bound(Fr(8), 0, Fr(p))         # exact variant: v * (Q mod p), v <= number of input limbs
+        assert acc <= LIMIT                        # the sum is exact
+        assert fold_bound(acc, Fr(p)) < p          # canon(): fold, + p, one conditional subtraction
+        worst = max(worst, acc / p)
+    for q in set(qs_in) | set(ps_out):
+        t = mul_bound(Fr(q), 0, Fr(q))
+        assert t < q and t + q < 2 * q             # f64_mul_canonical: r + q in (0, 2q)
+    return float(worst)
+
+
 def plan(logn, loge):
     npass = (logn + loge - 1) // loge
     first = logn - (npass - 1) * loge
@@ -100,10 +126,15 @@ def check_all():
                 pl = plan(logn, loge)
                 res[(q, logn, loge)] = (forward(pl, Fr(q)), inverse(list(reversed(pl)), Fr(q)))
         assert mac_budget(Fr(q)) < 8.0
+    # base conversion / pointwise product: eight worst-case input limbs against worst-case and small output moduli
+    res[(0, 0, 0)] = (canonical_product_budget([QMAX] * 8, [QMAX, (1 << 49) + 1, 3, 65537]), 0.0)
     return res
 
 
 if __name__ == "__main__":
     for k, v in sorted(check_all().items()):
-        print(k, "max |value|/q  fwd %.3f  inv %.3f" % v)
+        if k == (0, 0, 0):
+            print("canonical products (base conversion, reduce_mul): max |sum| / modulus %.3f" % v[0])
+        else:
+            print(k, "max |value|/q  fwd %.3f  inv %.3f" % v)
     print("all exactness preconditions hold for q <=", QMAX)
