@@ -452,10 +452,21 @@ __global__ void __launch_bounds__(256) baseconv_kernel(const __grid_constant__ B
                 if (EXACT) agg = __dadd_rn(agg, __ddiv_rn(word_to_double<T>(y[i]), c.q_f[i]));
             }
             for (int k = 0; k < n_out; k++) {
-                W acc = 0;
+                T r;
+                if constexpr (NIN <= 4) {
+                    // few terms: lazy Shoup products (1 high + 2 low multiplies each, any word-sized y) kept in [0, 2p) beat the double-word
+                    // dot product + two-word Barrett reduction (7 multiplies on its own); p < 2^(BITS-2), so 4p does not overflow
+                    const T pk = c.out_br[k].q, two_p = pk + pk;
+                    T acc = 0;
 #pragma unroll
-                for (int i = 0; i < NIN; i++) acc += (W)y[i] * c.matrix[k][i];
-                T r = barrett_reduce_wide(c.out_br[k], (T)acc, (T)(acc >> (sizeof(T) * 8)));
+                    for (int i = 0; i < NIN; i++) acc = csub<T>(acc + shoup_lazy<T>(y[i], c.matrix[k][i], c.matrix_q[k][i], pk), two_p);
+                    r = csub<T>(acc, pk);
+                } else {
+                    W acc = 0;
+#pragma unroll
+                    for (int i = 0; i < NIN; i++) acc += (W)y[i] * c.matrix[k][i];
+                    r = barrett_reduce_wide(c.out_br[k], (T)acc, (T)(acc >> (sizeof(T) * 8)));
+                }
                 if (EXACT) {
                     const T v = double_to_word<T>(__dadd_rn(agg, 0.5));
                     r = mod_sub<T>(r, barrett_mul<T>(c.out_br[0], v, c.q_mod_p[0]), c.out_br[0].q);
@@ -682,6 +693,7 @@ template <typename T> int make_baseconv(const T *in_moduli, size_t n_in, const T
         for (size_t i = 0; i < n_in; i++) {
             std::vector<T> p(in.punct[i], in.punct[i] + in.value_len);
             c.matrix[k][i] = hbig_mod_word<T>(p, out_moduli[k]);
+            c.matrix_q[k][i] = host::shoup_quot<T>(c.matrix[k][i], out_moduli[k]);
         }
         c.q_mod_p[k] = hbig_mod_word<T>(prod, out_moduli[k]);
         c.out_p_f[k] = (double)out_moduli[k];

@@ -28,6 +28,7 @@ template <typename T> struct BaseConvDev {
     T inv[kRnsMaxLimbs], inv_q[kRnsMaxLimbs];      // (Q/q_i)^-1 mod q_i and its Shoup quotient
     Barrett<T> in_br[kRnsMaxLimbs], out_br[kRnsMaxLimbs];
     T matrix[kRnsMaxLimbs][kRnsMaxLimbs];          // [output k][input i]
+    T matrix_q[kRnsMaxLimbs][kRnsMaxLimbs];        // Shoup quotient of matrix[k][i] for the modulus p_k (integer path with few input limbs)
     T q_mod_p[kRnsMaxLimbs];
     double q_f[kRnsMaxLimbs];
     // FP64-pipe formulation (u64 words, every modulus <= 2^50 - 2^10): the same constants as exact doubles
