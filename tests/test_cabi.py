@@ -178,3 +178,20 @@ def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
         pytest.skip("GPU present: the run itself is covered by tests/test_gpu_ext.py")
     p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0 and "failed" in p.stderr and "smoke ok" not in p.stdout
+
+
+def test_documented_environment_hooks_exist_in_the_sources():
+    """DESIGN.md section 10 lists the A/B switches; every one of them must be read somewhere under csrc/ (and vice versa for the PFHE_* getenv
+    calls), so the table cannot drift from the code."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    section = design[design.index("## 10. Environment hooks"):design.index("## 11.")]
+    documented = set(re.findall(r"`(PFHE_[A-Z0-9_]+)", section))
+    src = ""
+    csrc = os.path.join(root, "primus_fhe_b200", "csrc")
+    for f in os.listdir(csrc):
+        src += open(os.path.join(csrc, f)).read()
+    read = set(re.findall(r'getenv\("(PFHE_[A-Z0-9_]+)"\)', src)) | set(re.findall(r'env_int(?:_early)?\("(PFHE_[A-Z0-9_]+)"', src))
+    assert documented <= read, sorted(documented - read)
+    assert read <= documented, sorted(read - documented)
